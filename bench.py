@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 Verlet-list builder.
+
+  python bench.py --gpus 1 --steps K --warmup W            # our arm (1 GPU)
+  torchrun ... bench.py --gpus N --steps K --warmup W       # our arm, N ranks (slab decomposition + NCCL halo)
+  python bench.py --impl reference --steps K --warmup W     # the reference's own CPU classes (oracle/_ref)
+
+A "step" is one complete list build (cell binning, pair search, CSR emission) of one batch of synthetic particles.
+N=1 workload = BASELINE.json configs[1]: the reference default system at density 1.0 (make_list.cpp:17-24: L=50,
+search length 3.3, jittered FCC from mt19937(2), N=119164), double precision, FULL list (GPU semantics,
+kernel_impl.cuh:3-35) in CSR.  N>1: the same system replicated along z (one 50^3 slab per GPU) with ghost exchange.
+
+metric  = unordered neighbour pairs listed per second (whole job); the CPU reference lists the same pairs (half list).
+value   = positions already resident in HBM when the timed region starts; L2 is flushed between timed builds.
+e2e     = same build through the public API from pinned HOST buffers: H2D of positions, build, D2H of counts,
+          offsets and the partner list inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SL = 3.3
+L_DEFAULT = 50.0
+METRIC = "neighbor_pairs_listed_per_s"
+UNIT = "pairs/s"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        self._t = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self._t = threading.Thread(target=self._read, daemon=True)
+        self._t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU baseline (oracle/_ref = the reference's own classes; falls back to the oracle port)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(q, loops: int, variants=None):
+    """Times the reference's CPU classes on q; returns {variant: ms_per_build}, pairs, kind."""
+    from oracle import oracle as O
+    out = {}
+    pairs = None
+    kind = "reference"
+    variants = variants or ["avx512_8x1", "avx2_4x1", "scalar"]
+    for v in variants:
+        if not O.ref_available(v):
+            continue
+        r, ms = O.ref_build(v, q, SL, (L_DEFAULT, L_DEFAULT, L_DEFAULT), loops=loops)
+        out[v] = ms
+        pairs = r.number_of_pairs
+    if not out:  # oracle/_ref absent (should not happen on the GPU box: the .so files travel)
+        kind = "port"
+        t0 = time.perf_counter()
+        for _ in range(loops):
+            r = O.build_half(q, SL, (L_DEFAULT, L_DEFAULT, L_DEFAULT))
+        out["oracle_port_scalar"] = (time.perf_counter() - t0) * 1e3 / loops
+        pairs = r.number_of_pairs
+    return out, pairs, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    q = O.gen_fcc(1.0)
+    best_name, best_ms, times = None, None, {}
+    # pick the fastest variant with one probe build, then time `steps` builds of it
+    probe, pairs, kind = cpu_reference_run(q, 1)
+    best_name = min(probe, key=probe.get)
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_run(q, 1, [best_name])
+    t_tot = 0.0
+    for _ in range(args.steps):
+        r, _, _ = cpu_reference_run(q, 1, [best_name])
+        t_tot += r[best_name]
+    ms = t_tot / args.steps
+    val = pairs / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(1),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind,
+                         "sample": f"{args.steps} full builds of the density-1.0 default system with the reference's "
+                                   f"{best_name} class (single-threaded by construction); probe ms/build: "
+                                   + ", ".join(f"{k}={v:.1f}" for k, v in probe.items())},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "host": {"nproc": os.cpu_count()},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {"workload": "reference default system (make_list.cpp:17-24): jittered FCC, density 1.0, L=50, "
+                        "search length 3.3 (rc 3.0 + margin 0.3), N=119164 per GPU"
+                        + ("" if n_gpus == 1 else f", {n_gpus} slabs stacked along z with ghost exchange"),
+            "list": "full (both directions), CSR, int64 offsets", "particles_per_gpu": 119164,
+            "l2": "flushed between timed builds (256 MiB write)", "parallelism": f"slab{n_gpus}"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from md_neighbor_list_b200 import VerletListB200, workloads
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    L = L_DEFAULT
+    if world == 1:
+        q = workloads.fcc(1.0, L)
+        n_owned = q.shape[0]
+        box = (L, L, L)
+        halo = None
+    else:
+        from md_neighbor_list_b200 import parallel
+        halo = parallel.SlabDecomposition(world, rank, box=(L, L, L * world), search_length=SL, axis=2)
+        q = halo.local_fcc_slab(1.0, L)  # this rank's owned particles (global order), host
+        n_owned = q.shape[0]
+        box = (L, L, L * world)
+
+    stream = torch.cuda.Stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush_l2():
+        flush.fill_(1)
+
+    q_pinned = torch.from_numpy(q).pin_memory()
+    q_dev = q_pinned.to(dev, non_blocking=False)
+
+    nl = VerletListB200(SL, *box, dtype="f64", mode="full_csr")
+    cap_particles = n_owned if halo is None else n_owned + halo.max_ghosts(n_owned)
+    nl.initialize(cap_particles)
+
+    def one_build(qd_local=None):
+        if halo is None:
+            nl.build(q_dev, stream=stream)
+        else:
+            halo.build(nl, q_dev, stream)
+
+    # ---- warm-up ----
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            one_build()
+    st = nl.synchronize()
+    pairs_local = st.number_of_pairs // 2
+    entries_local = st.number_of_pairs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: K builds, device-timed, L2 flushed before each ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t0 = time.time()
+    with torch.cuda.stream(stream):
+        for k in range(args.steps):
+            flush_l2()
+            ev[k][0].record(stream)
+            one_build()
+            ev[k][1].record(stream)
+    barrier()
+    t1 = time.time()
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    ms_total = float(sum(ms_steps))
+    # hot-L2 protocol of the reference drivers (LOOP identical builds back to back, make_list.cu:124-130)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            one_build()
+        e1.record(stream)
+    barrier()
+    ms_hot = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop(t0, t1)
+
+    # ---- e2e: host buffers in, host buffers out ----
+    st = nl.synchronize()
+    n_entries = st.number_of_pairs
+    h_cnt = torch.empty(n_owned, dtype=torch.int32).pin_memory()
+    h_off = torch.empty(n_owned + 1, dtype=torch.int64).pin_memory()
+    h_lst = torch.empty(n_entries, dtype=torch.int32).pin_memory()
+    q_dev2 = torch.empty_like(q_dev)
+
+    def one_e2e():
+        q_dev2.copy_(q_pinned, non_blocking=True)
+        if halo is None:
+            nl.build(q_dev2, stream=stream)
+        else:
+            halo.build(nl, q_dev2, stream)
+        h_cnt.copy_(nl.number_of_partners(), non_blocking=True)
+        h_off.copy_(nl.offsets(), non_blocking=True)
+        h_lst.copy_(nl.partners()[:n_entries], non_blocking=True)
+
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            one_e2e()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 20))
+    w0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            one_e2e()
+        e1.record(stream)
+    barrier()
+    w1 = time.perf_counter()
+    ms_e2e = max(e0.elapsed_time(e1), (w1 - w0) * 1e3) / e2e_steps
+    assert int(h_off[-1]) == n_entries and int(h_cnt.sum()) == n_entries
+
+    # ---- dominant kernel: per-stage device times (separate, profiled handle; L2 flushed) ----
+    stage_ms = {}
+    if rank == 0:
+        nlp = VerletListB200(SL, *box, dtype="f64", mode="full_csr", profile=True)
+        nlp.initialize(cap_particles)
+        reps = 10
+        for r in range(reps + 2):
+            with torch.cuda.stream(stream):
+                flush_l2()
+                if halo is None:
+                    nlp.build(q_dev, stream=stream)
+                else:
+                    halo.build(nlp, q_dev, stream)
+            nlp.synchronize()
+            if r >= 2:
+                for k, v in nlp.stage_times().items():
+                    stage_ms[k] = stage_ms.get(k, 0.0) + v / reps
+        nlp.close()
+
+    # ---- reduce over ranks ----
+    vals = torch.tensor([ms_total, ms_hot, ms_e2e], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(pairs_local), float(entries_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    ms_total, ms_hot, ms_e2e = [float(v) for v in vals.cpu()]
+    pairs_all, entries_all = [float(v) for v in sums.cpu()]
+
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        value = pairs_all / (ms_step * 1e-3)
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        n = n_owned
+        # algorithmic bytes: B_alg = N*(V+8) + 4*P per build, V = 32 (double4)
+        b_alg_build = n * (32 + 8) + 4 * entries_local
+        # the dominant kernel (search_fill) reads one 16-B record + one 8-B offset per particle, writes 4 B per entry
+        b_alg_fill = n * (16 + 8) + 4 * entries_local
+        fill_ms = stage_ms.get("search_fill")
+        roof = {"bound": "hbm", "kernel": "search_kernel<FILL>", "achieved": None, "peak": peak, "unit": "GB/s",
+                "frac": None, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b_alg_fill}
+        if fill_ms:
+            roof["achieved"] = b_alg_fill / (fill_ms * 1e-3) / 1e9
+            roof["frac"] = roof["achieved"] / peak
+            roof["kernel_ms"] = fill_ms
+        build_gbs = b_alg_build / (ms_step * 1e-3) / 1e9
+        q_host_np = q
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            qref = np.ascontiguousarray(q_host_np)
+            times, cpairs, kind = cpu_reference_run(qref, args.cpu_loops)
+            best = min(times, key=times.get)
+            cpu = {"value": cpairs / (times[best] * 1e-3), "unit": UNIT, "cores": 1, "kind": kind,
+                   "sample": f"{args.cpu_loops} full builds per variant of the same density-1.0 default system, "
+                             f"reference classes compiled from the reference sources (oracle/_ref), 1 thread "
+                             f"(the reference is single-threaded); ms/build: "
+                             + ", ".join(f"{k}={v:.1f}" for k, v in times.items()),
+                   "ms_per_build": times, "host_nproc": os.cpu_count()}
+        kernels_per_build = 7
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world),
+            "clocks": clocks,
+            "e2e": {"value": pairs_all / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(q_pinned.numel() * 8),
+                    "d2h_bytes_per_step": int(h_cnt.numel() * 4 + h_off.numel() * 8 + h_lst.numel() * 4)},
+            "gpu_launches": kernels_per_build * args.steps,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "build": {"ms_cold_l2": ms_step, "ms_hot_l2_back_to_back": ms_hot,
+                      "entries_per_s": entries_all / (ms_step * 1e-3),
+                      "candidate_tests_per_s": st.candidates_tested * 2 / (ms_step * 1e-3),
+                      "candidates_per_pass": st.candidates_tested, "band_retests": st.band_tests,
+                      "algorithmic_bytes": b_alg_build, "algorithmic_gbs": build_gbs,
+                      "frac_of_hbm_peak": build_gbs / peak, "stage_ms": stage_ms,
+                      "ms_per_step_each": ms_steps if len(ms_steps) <= 32 else ms_steps[:32]},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-loops", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

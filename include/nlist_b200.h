@@ -1,0 +1,215 @@
+/*
+ * nlist_b200.h — C ABI of the B200-native Verlet neighbor-list builder (libnlist_b200.so).
+ *
+ * This is the drop-in boundary for the list-build path of kohnakagawa/md_neighbor_list.  The reference has no FFI:
+ * its boundary is the header-only C++ class instantiated by the drivers.  Every entry point below
+ * names the reference interface it replaces (file:line relative to the reference root); include/nlist_b200_shim.hpp
+ * re-creates the reference's class/method names on top of this ABI so that a make_list.cu / make_list.cpp shaped
+ * driver compiles against either implementation.
+ *
+ * Conventions
+ *   - plain C types only; device pointers are raw `void*` / typed pointers into CUDA device memory;
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every call returns an nlb200_status (0 = ok).  nlb200_last_error() gives the message of the last failure on
+ *     that handle.  Capacity overflow is DETECTED and reported (the reference's fixed capacities overflow silently:
+ *     neighlist_cpu.hpp:37,76-78; neighlist_gpu.hpp:70,74,102,111).
+ *   - the handle owns all outputs; getters return borrowed device pointers valid until the next build / reserve /
+ *     destroy on that handle (reference ownership: neighlist_gpu.hpp:94-123, accessors 468-487).
+ *   - per-handle state, no globals: any number of handles may live in one process (the reference allows one,
+ *     neighlist_gpu.hpp:15-18,303).
+ *   - no CPU fallback exists: every entry point that computes needs a CUDA device and fails with
+ *     NLB200_ERR_CUDA otherwise.
+ *
+ * Semantics preserved from the reference (SURVEY.md §8b "Semantics to preserve")
+ *   - open boundary: cell indices are clamped, distances are plain Euclidean (neighlist_cpu.hpp:219-223,
+ *     kernel_impl.cuh:25-29) — no minimum image.
+ *   - accept a pair iff !(r2 > SL2), r2 = fma(dz,dz, fma(dy,dy, dx*dx)) evaluated in the input precision
+ *     (the contraction nvcc/g++ apply to `drx*drx + dry*dry + drz*drz`, kernel_impl.cuh:28, neighlist_cpu.hpp:222),
+ *     SL2 = SL*SL rounded once in the input precision (neighlist_gpu.hpp:254, neighlist_cpu.hpp:394).
+ *   - partner ids index the caller's array; the caller's array is never permuted.
+ *   - HALF: row i holds the partners j > i (neighlist_cpu.hpp:225-236).  FULL: every j != i (kernel_impl.cuh:29).
+ */
+#ifndef NLIST_B200_H_
+#define NLIST_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLB200_VERSION 100
+
+typedef struct nlb200_context* nlb200_handle;
+
+typedef enum {
+  NLB200_OK = 0,
+  NLB200_ERR_INVALID = 1,     /* bad argument / precondition (e.g. fewer than 3 cells on an axis) */
+  NLB200_ERR_CUDA = 2,        /* CUDA runtime failure or no device */
+  NLB200_ERR_CAPACITY = 3,    /* partner-list capacity too small; nlb200_required_entries() tells how much */
+  NLB200_ERR_OUT_OF_BOX = 4,  /* a particle lies more than one cell outside [0,L] (or is NaN) */
+  NLB200_ERR_ELL_ROWS = 5,    /* a row is longer than the ELL row capacity (reference: silent overflow) */
+  NLB200_ERR_STATE = 6        /* call order violated (e.g. build before initialize) */
+} nlb200_status;
+
+/* Position element type — the reference's `Dtype` toggle, make_list.cu:6-12. */
+typedef enum { NLB200_F32 = 0, NLB200_F64 = 1 } nlb200_dtype;
+
+/* Output structure.
+ *   HALF_CSR            : NeighList / NeighListAVX2 / NeighListAVX512 (neighlist_cpu.hpp:361-377) — each pair once,
+ *                         keyed by the smaller index.
+ *   FULL_CSR            : the rows of NeighListGPU (kernel_impl.cuh:3-35) stored in CSR.
+ *   FULL_ELL_TRANSPOSED : FULL_CSR plus the reference GPU layout list[k*N + i], padded with -1
+ *                         (kernel_impl.cuh:30, neighlist_gpu.hpp:271-274, consumed at make_list.cu:178-182). */
+typedef enum { NLB200_HALF_CSR = 0, NLB200_FULL_CSR = 1, NLB200_FULL_ELL_TRANSPOSED = 2 } nlb200_mode;
+
+typedef enum {
+  /* elements per position record: 4 = {x,y,z,w} (double4/float4, make_list.cu:8,11; AVX Vec make_list.cpp:28),
+   * 3 = {x,y,z} (scalar CPU Vec, make_list.cpp:30).  Default 4. */
+  NLB200_OPT_POSITION_STRIDE = 1,
+  /* 0 (default): rows in deterministic stencil order (cell-major, ids ascending inside a cell) — the order the
+   * reference kernels discover partners in.  1: rows sorted ascending by partner id (what the reference tests
+   * do before comparing, make_list.cpp:120-128,211; make_list.cu:183-184). */
+  NLB200_OPT_SORT_ROWS = 2,
+  /* row capacity of the ELL-transposed view — the reference's MAX_PARTNERS (neighlist_gpu.hpp:70-71). Default 200. */
+  NLB200_OPT_ELL_ROWS = 3,
+  /* 1: skip the FP32 pre-filter and run the exact input-precision test on every candidate (validation only). */
+  NLB200_OPT_EXACT_ONLY = 4,
+  /* 1 (default): replay the build as a CUDA graph when (q, n, stream) repeat. 0: plain launches. */
+  NLB200_OPT_USE_GRAPH = 5,
+  /* search-kernel variant selector for tuning/ablation (0 = default). */
+  NLB200_OPT_KERNEL_VARIANT = 6,
+  /* 1: record a CUDA event between the stages of every build on the build's stream (disables graph replay);
+   * read the per-stage device times with nlb200_get_stage_times.  The reference's counterpart is
+   * `make cuda_profile=yes` + nvprof (Makefile:21,29-31). */
+  NLB200_OPT_PROFILE = 7
+} nlb200_option;
+
+typedef struct {
+  int64_t n;                   /* particles of the last build */
+  int64_t number_of_pairs;     /* emitted list entries (HALF: pairs, FULL: 2 x pairs) */
+  int64_t candidates_tested;   /* distance tests evaluated by one search pass */
+  int64_t band_tests;          /* candidates that fell in the FP32 pre-filter's uncertainty band and were re-tested
+                                  exactly in the input precision */
+  int64_t required_entries;    /* entries the last build needed (valid also after NLB200_ERR_CAPACITY) */
+  int64_t capacity_entries;    /* current partner-list capacity */
+  int32_t mesh[3];             /* cells per axis (neighlist_cpu.hpp:384-387) */
+  int32_t max_partners;        /* longest row */
+  int32_t max_in_cell;         /* most populated cell (reference: nmax_in_mesh_, neighlist_gpu.hpp:169) */
+  int32_t reserved;
+} nlb200_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------------ */
+
+/* Replaces the constructors NeighListGPU(search_length, Lx, Ly, Lz) (neighlist_gpu.hpp:236-255) and
+ * NeighList*(search_length, Lx, Ly, Lz) (neighlist_cpu.hpp:380-395).  search_length already includes the margin
+ * (make_list.cpp:23).  mesh_size = int(L / search_length) must be >= 3 on every axis. */
+int nlb200_create(double search_length, double lx, double ly, double lz, int dtype, int mode, nlb200_handle* out);
+
+/* Compile-time -D switches / edited constants of the reference (Makefile:64-119, neighlist_gpu.hpp:70-75) become
+ * run-time options.  Must be called before nlb200_initialize. */
+int nlb200_set_option(nlb200_handle h, int option, int64_t value);
+
+/* Replaces Initialize(particle_number) (neighlist_gpu.hpp:268-287, neighlist_cpu.hpp:408-415): allocates for up to
+ * max_particles.  max_entries is the partner-list capacity; 0 = estimate from the density max_particles/(Lx*Ly*Lz)
+ * (the reference hand-edits MAX_PARTNERS per density, neighlist_gpu.hpp:70-71). */
+int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entries);
+
+/* Grow (never shrink) the partner-list capacity; invalidates borrowed pointers. */
+int nlb200_reserve(nlb200_handle h, int64_t max_entries);
+
+/* Replaces the destructors (neighlist_gpu.hpp:256-258, neighlist_cpu.hpp:396-398). */
+int nlb200_destroy(nlb200_handle h);
+
+/* ---- the hot path --------------------------------------------------------------------------------------------- */
+
+/* Replaces NeighListGPU::MakeNeighList(q, particle_number, sync=false, ...) (neighlist_gpu.hpp:289-466) and
+ * NeighList*::MakeNeighList(q, particle_number) (neighlist_cpu.hpp:417-435).
+ * q_dev: device pointer to n position records in the handle's dtype and stride.  Asynchronous on `stream`; no host
+ * synchronisation happens inside.  Device-side failures (capacity, out-of-box) surface at nlb200_synchronize. */
+int nlb200_build(nlb200_handle h, const void* q_dev, int64_t n, void* stream);
+
+/* Multi-GPU form (no reference counterpart): q_dev holds n_total = owned + ghost records, rows are
+ * emitted only for the first n_owned; if global_ids_dev != NULL partner ids (and the HALF-mode j > i rule) use
+ * global_ids_dev[local index] instead of the local index. */
+int nlb200_build_subset(nlb200_handle h, const void* q_dev, int64_t n_total, int64_t n_owned,
+                        const int32_t* global_ids_dev, void* stream);
+
+/* Replaces the `sync` argument / cudaDeviceSynchronize of neighlist_gpu.hpp:465 and make_list.cu:128: waits for the
+ * last build on its stream, fetches the device status word and statistics.  Returns the build's status. */
+int nlb200_synchronize(nlb200_handle h);
+
+/* Convenience for host callers (the shape of the CPU classes, make_list.cpp:143-163): H2D copy of q_host, build,
+ * synchronize, grow-and-retry on NLB200_ERR_CAPACITY, D2H of the outputs the caller asks for (NULL = skip).
+ * offsets_host receives n+1 int64 values; partners_host must hold partners_capacity entries. */
+int nlb200_build_host(nlb200_handle h, const void* q_host, int64_t n, int32_t* number_of_partners_host,
+                      int64_t* offsets_host, int32_t* partners_host, int64_t partners_capacity,
+                      int64_t* number_of_pairs);
+
+/* ---- accessors (borrowed device pointers) --------------------------------------------------------------------- */
+
+/* number_of_partners() — neighlist_gpu.hpp:476-482, neighlist_cpu.hpp:455-461.  int32[n]. */
+const int32_t* nlb200_number_of_partners(nlb200_handle h);
+/* key_pointer() — neighlist_cpu.hpp:447-453; 64-bit because 16M particles x ~150 partners exceeds INT32_MAX
+ * (SURVEY.md §7 "Index width").  int64[n+1]. */
+const int64_t* nlb200_offsets(nlb200_handle h);
+/* 32-bit view of the offsets for reference-shaped callers; NULL (and NLB200_ERR_INVALID from
+ * nlb200_synchronize-time check) when the total exceeds INT32_MAX.  int32[n+1]. */
+const int32_t* nlb200_offsets32(nlb200_handle h);
+/* sorted_list() — neighlist_cpu.hpp:439-445; rows of the FULL list for the GPU modes.  int32[number_of_pairs]. */
+const int32_t* nlb200_partners(nlb200_handle h);
+/* neigh_list() — neighlist_gpu.hpp:468-474: list[k*n + i], k < ell_rows, -1 padded.  Only in
+ * NLB200_FULL_ELL_TRANSPOSED mode, else NULL. */
+const int32_t* nlb200_ell_transposed(nlb200_handle h);
+/* number_of_pairs() — neighlist_gpu.hpp:484-487 (thrust::reduce), neighlist_cpu.hpp:437.  Needs a prior
+ * nlb200_synchronize; returns -1 otherwise. */
+int64_t nlb200_number_of_pairs(nlb200_handle h);
+
+/* Cell-binning results, exposed for parity tests and for downstream kernels that want cell-sorted access
+ * (reference: mesh_index_ / ptcl_id_in_mesh_, neighlist_cpu.hpp:146-165,
+ * neighlist_gpu.hpp:153-199).  cell_start: int32[M+1]; sorted_ids: int32[n], ids ascending inside a cell. */
+const int32_t* nlb200_cell_start(nlb200_handle h);
+const int32_t* nlb200_sorted_ids(nlb200_handle h);
+
+int nlb200_get_stats(nlb200_handle h, nlb200_stats* out);
+/* Per-stage device times of the last (synchronized) build when NLB200_OPT_PROFILE is on: fills ms_out/stage_ids_out
+ * (up to `capacity` stages, in execution order) and returns the stage count, or -1. */
+int nlb200_get_stage_times(nlb200_handle h, float* ms_out, int32_t* stage_ids_out, int capacity);
+const char* nlb200_stage_name(int stage_id);
+int64_t nlb200_required_entries(nlb200_handle h);
+const char* nlb200_last_error(nlb200_handle h);
+const char* nlb200_status_string(int status);
+int nlb200_version(void);
+
+/* ---- adjacent utilities (device side of the drivers) ---------------------------------------------------------- */
+
+/* Ghost selection for slab decomposition: writes the indices i < n with lo <= q[i][axis] < hi into
+ * out_idx_dev (ascending, deterministic) and the count into *out_count_dev.  capacity = size of out_idx_dev. */
+int nlb200_select_slab(const void* q_dev, int64_t n, int dtype, int stride, int axis, double lo, double hi,
+                       int32_t* out_idx_dev, int64_t capacity, int64_t* out_count_dev, void* workspace_dev,
+                       int64_t workspace_bytes, void* stream);
+
+/* Bytes of workspace nlb200_select_slab needs for n particles. */
+int64_t nlb200_select_slab_workspace(int64_t n);
+
+/* Gathers position records: dst[k] = src[idx[k]] (stride elements each). */
+int nlb200_gather_records(const void* src_dev, const int32_t* idx_dev, int64_t count, int dtype, int stride,
+                          void* dst_dev, void* stream);
+
+/* ---- workload generators (host; mirror the reference drivers, not part of the list build) ---------------------- */
+
+/* make_list.cpp:51-77 / make_list.cu:42-66 `init`: jittered FCC lattice, `std::mt19937 mt(seed)` (the reference uses
+ * 2), U[0,0.1) jitter drawn x,y,z.  sx/sy/sz <= 0 -> int(L/s) as in the reference.  Writes `stride` doubles per
+ * particle (w = 0).  q == NULL returns the particle count. */
+int64_t nlb200_workload_fcc(double density, double L, int sx, int sy, int sz, uint32_t seed, double* q, int stride,
+                            int64_t capacity);
+/* x,y,z ~ U[0,L) from std::mt19937_64(seed). */
+int64_t nlb200_workload_uniform(int64_t n, double L, uint64_t seed, double* q, int stride);
+/* 50 % uniform background + 50 % in `blobs` isotropic Gaussian blobs (sigma = L/40, centres
+ * uniform, reflected into [0,L)), std::mt19937_64(seed). */
+int64_t nlb200_workload_clustered(int64_t n, double L, int blobs, uint64_t seed, double* q, int stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLIST_B200_H_ */

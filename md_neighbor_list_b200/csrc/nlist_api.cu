@@ -1,0 +1,756 @@
+// nlist_api.cu — host side of libnlist_b200.so: the C ABI declared in include/nlist_b200.h.
+//
+// The reference's host logic lives in NeighListGPU (neighlist_gpu.hpp:43-488): constructor (236-255), Allocate
+// (94-112), Initialize (268-287), MakeNeighList (289-466), accessors (468-487).  This file is its B200-native
+// counterpart: per-handle state instead of globals/statics, one stream-ordered kernel chain with no host
+// synchronisation inside a build, the chain replayed as a CUDA graph, capacities checked on the device and reported.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/nlist_b200.h"
+#include "nlist_kernels.cuh"
+
+using namespace nlb;
+
+struct nlb200_context {
+  // configuration
+  double sl = 0, L[3] = {0, 0, 0};
+  int dtype = NLB200_F64, mode = NLB200_FULL_CSR;
+  int stride = 4, sort_rows = 0, ell_rows = 200, exact_only = 0, use_graph = 1, variant = 0, profile = 0;
+  GridParams<double> gp64;
+  GridParams<float> gp32;
+  int32_t mesh[3] = {0, 0, 0};
+  int64_t n_cells = 0;
+  bool initialized = false;
+  int device = 0;
+
+  // capacities
+  int64_t max_n = 0, cap_entries = 0;
+  int64_t tiles_cells = 0, tiles_n = 0;
+
+  // device buffers
+  unsigned char* zero_region = nullptr;  // [cell_count | scan state (cells) | scan state (counts) | status]
+  size_t zero_bytes = 0;
+  int32_t* cell_count = nullptr;
+  unsigned long long* scan_state_cells = nullptr;
+  unsigned long long* scan_state_counts = nullptr;
+  DeviceStatus* status_dev = nullptr;
+  int32_t* cell_start = nullptr;
+  int2* cell_rank = nullptr;
+  int32_t* perm = nullptr;
+  int32_t* sorted_ids = nullptr;
+  float4* rec = nullptr;
+  int32_t* counts = nullptr;
+  int64_t* offsets = nullptr;
+  int32_t* offsets32 = nullptr;
+  int32_t* partners = nullptr;
+  int32_t* ell = nullptr;
+  int32_t* ell_prev = nullptr;
+  int64_t ell_last_n = -1;  // row stride of the ELL view written by the previous build
+  void* q_stage = nullptr;  // device staging for nlb200_build_host
+  cudaStream_t own_stream = nullptr;
+
+  // host mirrors
+  DeviceStatus* status_host = nullptr;  // pinned
+  cudaStream_t last_stream = nullptr;
+  bool build_pending = false;
+  bool have_result = false;
+  int64_t last_n = 0, last_owned = 0;
+  nlb200_stats stats{};
+
+  // graph cache (one entry: the reference's usage is LOOP identical builds, make_list.cu:124-127)
+  cudaGraphExec_t graph_exec = nullptr;
+  const void* g_q = nullptr;
+  const int32_t* g_gids = nullptr;
+  int64_t g_n = -1, g_owned = -1;
+
+  // per-stage CUDA events (NLB200_OPT_PROFILE): ev[k] is recorded before stage k, ev[n_stages] after the last one
+  static constexpr int MAX_STAGES = 12;
+  cudaEvent_t ev[MAX_STAGES + 1] = {};
+  int stage_id[MAX_STAGES] = {};
+  int n_stages = 0;
+
+  std::string err;
+};
+
+enum StageId { ST_ZERO = 0, ST_BIN, ST_SCAN_CELLS, ST_SCATTER, ST_CELLSORT, ST_COUNT, ST_SCAN_COUNTS, ST_FILL,
+               ST_SORT_ROWS, ST_ELL, ST_STATUS, ST_NUM };
+static const char* const kStageNames[ST_NUM] = {"zero", "bin", "scan_cells", "scatter", "cellsort", "search_count",
+                                                "scan_counts", "search_fill", "sort_rows", "ell", "status_copy"};
+
+namespace {
+
+int fail(nlb200_context* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+
+#define CK(h, call)                                                                                     \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return fail(h, NLB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                            \
+  } while (0)
+
+template <typename T>
+bool make_grid(double sl, const double* L, GridParams<T>* g) {
+  // neighlist_gpu.hpp:240-254 evaluated in T (the reference's Dtype)
+  const T slt = (T)sl;
+  T msmax = 0;
+  int64_t cells = 1;
+  for (int d = 0; d < 3; d++) {
+    const T l = (T)L[d];
+    const int32_t m = (int32_t)(l / slt);
+    if (m < 3) return false;
+    g->mesh[d] = m;
+    g->ms[d] = l / (T)m;
+    g->ims[d] = (T)(1.0 / (double)g->ms[d]);
+    g->msf[d] = (float)g->ms[d];
+    if (g->ms[d] > msmax) msmax = g->ms[d];
+    cells *= m;
+  }
+  if (cells > 2000000000ll) return false;
+  g->n_cells = (int32_t)cells;
+  g->sl2 = slt * slt;
+  g->sl2f = (float)g->sl2;
+  // Half-width E of the pre-filter band, in units of (SL2 - r2)/2.  DESIGN.md derives
+  //   E <= u * ms_max^2 * ~216 (FP32 evaluation + coordinate rounding) + 16 u SL2 (FP32 reference evaluation)
+  // with u = 2^-24; 384 u ms_max^2 leaves > 1.5x slack.
+  g->band = (float)(384.0 * std::ldexp(1.0, -24) * (double)msmax * (double)msmax);
+  return true;
+}
+
+void free_buffers(nlb200_context* h) {
+  auto F = [](auto*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  if (h->graph_exec) {
+    cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+  }
+  F(h->zero_region);
+  F(h->cell_start);
+  F(h->cell_rank);
+  F(h->perm);
+  F(h->sorted_ids);
+  F(h->rec);
+  F(h->counts);
+  F(h->offsets);
+  F(h->offsets32);
+  F(h->partners);
+  F(h->ell);
+  F(h->ell_prev);
+  F(h->q_stage);
+  if (h->status_host) cudaFreeHost(h->status_host);
+  h->status_host = nullptr;
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  h->own_stream = nullptr;
+  for (int k = 0; k <= nlb200_context::MAX_STAGES; k++) {
+    if (h->ev[k]) cudaEventDestroy(h->ev[k]);
+    h->ev[k] = nullptr;
+  }
+  h->initialized = false;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void drop_graph(nlb200_context* h) {
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  h->graph_exec = nullptr;
+  h->g_q = nullptr;
+  h->g_n = -1;
+}
+
+// ---- search-kernel dispatch -------------------------------------------------------------------------------------
+template <typename T, int STRIDE, bool HALF, bool FILL, bool EXACT>
+cudaError_t launch_search_t(const SearchArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
+  search_kernel<T, STRIDE, HALF, FILL, EXACT><<<grid, block, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+constexpr int MAX_SEARCH_SMEM = 200 * 1024;
+
+// opt every search-kernel instantiation into > 48 KB of dynamic shared memory (done once, outside graph capture)
+template <typename T, int STRIDE, bool HALF, bool FILL>
+cudaError_t set_attr_e() {
+  cudaError_t e = cudaFuncSetAttribute(search_kernel<T, STRIDE, HALF, FILL, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SEARCH_SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(search_kernel<T, STRIDE, HALF, FILL, true>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SEARCH_SMEM);
+}
+template <typename T, int STRIDE>
+cudaError_t set_attr_ts() {
+  cudaError_t e;
+  if ((e = set_attr_e<T, STRIDE, false, false>()) != cudaSuccess) return e;
+  if ((e = set_attr_e<T, STRIDE, false, true>()) != cudaSuccess) return e;
+  if ((e = set_attr_e<T, STRIDE, true, false>()) != cudaSuccess) return e;
+  return set_attr_e<T, STRIDE, true, true>();
+}
+cudaError_t set_search_attrs() {
+  cudaError_t e;
+  if ((e = set_attr_ts<double, 4>()) != cudaSuccess) return e;
+  if ((e = set_attr_ts<double, 3>()) != cudaSuccess) return e;
+  if ((e = set_attr_ts<float, 4>()) != cudaSuccess) return e;
+  return set_attr_ts<float, 3>();
+}
+
+template <typename T, int STRIDE, bool HALF, bool FILL>
+cudaError_t launch_search_e(bool exact, const SearchArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
+  return exact ? launch_search_t<T, STRIDE, HALF, FILL, true>(a, grid, block, smem, s)
+               : launch_search_t<T, STRIDE, HALF, FILL, false>(a, grid, block, smem, s);
+}
+
+template <typename T, int STRIDE>
+cudaError_t launch_search(bool half, bool fill, bool exact, const SearchArgs<T>& a, int grid, int block, size_t smem,
+                          cudaStream_t s) {
+  if (half)
+    return fill ? launch_search_e<T, STRIDE, true, true>(exact, a, grid, block, smem, s)
+                : launch_search_e<T, STRIDE, true, false>(exact, a, grid, block, smem, s);
+  return fill ? launch_search_e<T, STRIDE, false, true>(exact, a, grid, block, smem, s)
+              : launch_search_e<T, STRIDE, false, false>(exact, a, grid, block, smem, s);
+}
+
+template <typename T>
+const GridParams<T>& grid_of(const nlb200_context* h);
+template <>
+const GridParams<double>& grid_of<double>(const nlb200_context* h) {
+  return h->gp64;
+}
+template <>
+const GridParams<float>& grid_of<float>(const nlb200_context* h) {
+  return h->gp32;
+}
+
+// Enqueue one build on `s` (plain launches; the caller may be capturing them into a graph).
+template <typename T, int STRIDE>
+int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owned, const int32_t* gids,
+                  cudaStream_t s) {
+  const GridParams<T>& gp = grid_of<T>(h);
+  const int32_t n = (int32_t)n_total;
+  const int32_t M = gp.n_cells;
+  h->n_stages = 0;
+  auto stage = [&](int id) -> cudaError_t {
+    if (!h->profile) return cudaSuccess;
+    if (h->n_stages >= nlb200_context::MAX_STAGES) return cudaSuccess;
+    h->stage_id[h->n_stages] = id;
+    return cudaEventRecord(h->ev[h->n_stages++], s);
+  };
+  CK(h, stage(ST_ZERO));
+  CK(h, cudaMemsetAsync(h->zero_region, 0, h->zero_bytes, s));
+  CK(h, stage(ST_BIN));
+  if (n > 0) {
+    bin_kernel<T, STRIDE><<<(n + 255) / 256, 256, 0, s>>>(q, n, gp, h->cell_count, h->cell_rank, h->status_dev);
+    CK(h, cudaGetLastError());
+  }
+  CK(h, stage(ST_SCAN_CELLS));
+  {
+    const int tiles = (int)((M + SCAN_TILE - 1) / SCAN_TILE);
+    scan_kernel<int32_t><<<tiles, SCAN_THREADS, 0, s>>>(h->cell_count, M, h->cell_start, nullptr,
+                                                        h->scan_state_cells, nullptr, &h->status_dev->max_in_cell,
+                                                        0);
+    CK(h, cudaGetLastError());
+  }
+  CK(h, stage(ST_SCATTER));
+  if (n > 0) {
+    scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->cell_rank, n, h->cell_start, h->perm);
+    CK(h, cudaGetLastError());
+    CK(h, stage(ST_CELLSORT));
+    const int64_t threads = (int64_t)M * 32;
+    cellsort_kernel<T, STRIDE><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(q, gp, h->cell_start, h->perm,
+                                                                                 h->sorted_ids, h->rec);
+    CK(h, cudaGetLastError());
+  }
+  // search geometry from the mean occupancy (no host sync: the maximum is not known here)
+  const double avg = (double)n_total / (double)M;
+  int block = (int)(std::ceil(avg * 1.25 / 32.0) * 32.0);
+  if (block < 32) block = 32;
+  if (block > 128) block = 128;
+  int64_t jt = (int64_t)(27.0 * avg * 1.5);
+  jt = (jt + 255) / 256 * 256;
+  if (jt < 512) jt = 512;
+  if (jt > 8192) jt = 8192;
+  const size_t smem = (size_t)jt * (sizeof(float4) + sizeof(int32_t));
+
+  SearchArgs<T> a;
+  a.q = q;
+  a.gp = gp;
+  a.cell_start = h->cell_start;
+  a.rec = h->rec;
+  a.global_ids = gids;
+  a.n_owned = (int32_t)n_owned;
+  a.counts = h->counts;
+  a.offsets = h->offsets;
+  a.partners = h->partners;
+  a.capacity = h->cap_entries;
+  a.st = h->status_dev;
+  a.jt = (int32_t)jt;
+  const bool half = h->mode == NLB200_HALF_CSR;
+  CK(h, stage(ST_COUNT));
+  if (n > 0) {
+    CK(h, (launch_search<T, STRIDE>(half, false, h->exact_only != 0, a, M, block, smem, s)));
+  }
+  CK(h, stage(ST_SCAN_COUNTS));
+  {
+    const int tiles = (int)((n_owned + SCAN_TILE - 1) / SCAN_TILE);
+    scan_kernel<int64_t><<<tiles > 0 ? tiles : 1, SCAN_THREADS, 0, s>>>(
+        h->counts, n_owned, h->offsets, h->offsets32, h->scan_state_counts, h->status_dev,
+        &h->status_dev->max_partners, (long long)h->cap_entries);
+    CK(h, cudaGetLastError());
+  }
+  CK(h, stage(ST_FILL));
+  if (n > 0) {
+    CK(h, (launch_search<T, STRIDE>(half, true, h->exact_only != 0, a, M, block, smem, s)));
+  }
+  if (h->sort_rows) CK(h, stage(ST_SORT_ROWS));
+  if (h->sort_rows && n_owned > 0) {
+    sort_rows_kernel<<<(unsigned)((n_owned + SORT_WARPS - 1) / SORT_WARPS), SORT_WARPS * 32, 0, s>>>(
+        h->offsets, (int32_t)n_owned, h->partners, (long long)h->cap_entries);
+    CK(h, cudaGetLastError());
+  }
+  if (h->mode == NLB200_FULL_ELL_TRANSPOSED) CK(h, stage(ST_ELL));
+  if (h->mode == NLB200_FULL_ELL_TRANSPOSED && n_owned > 0) {
+    ell_kernel<<<(unsigned)((n_owned + 255) / 256), 256, 0, s>>>(h->offsets, h->partners, (int32_t)n_owned,
+                                                                h->ell_rows, h->ell, h->ell_prev,
+                                                                (long long)h->cap_entries, h->status_dev);
+    CK(h, cudaGetLastError());
+  }
+  CK(h, stage(ST_STATUS));
+  CK(h, cudaMemcpyAsync(h->status_host, h->status_dev, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, s));
+  if (h->profile) CK(h, cudaEventRecord(h->ev[h->n_stages], s));
+  return NLB200_OK;
+}
+
+int enqueue_dispatch(nlb200_context* h, const void* q, int64_t n_total, int64_t n_owned, const int32_t* gids,
+                     cudaStream_t s) {
+  if (h->dtype == NLB200_F64) {
+    return h->stride == 4 ? enqueue_build<double, 4>(h, (const double*)q, n_total, n_owned, gids, s)
+                          : enqueue_build<double, 3>(h, (const double*)q, n_total, n_owned, gids, s);
+  }
+  return h->stride == 4 ? enqueue_build<float, 4>(h, (const float*)q, n_total, n_owned, gids, s)
+                        : enqueue_build<float, 3>(h, (const float*)q, n_total, n_owned, gids, s);
+}
+
+int64_t estimate_entries(const nlb200_context* h, int64_t n) {
+  // expected entries ~ n * rho * (4/3) pi SL^3, +30 % and a floor for sparse boxes
+  const double vol = h->L[0] * h->L[1] * h->L[2];
+  const double rho = (double)n / vol;
+  double per = rho * 4.18879020478639 * h->sl * h->sl * h->sl;
+  if (h->mode == NLB200_HALF_CSR) per *= 0.5;
+  double e = (double)n * per * 1.3 + 16.0 * (double)n + 1024.0;
+  return (int64_t)e;
+}
+
+int alloc_partners(nlb200_context* h, int64_t entries) {
+  if (h->partners) cudaFree(h->partners);
+  h->partners = nullptr;
+  CK(h, cudaMalloc(&h->partners, sizeof(int32_t) * (size_t)(entries > 0 ? entries : 1)));
+  h->cap_entries = entries;
+  return NLB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nlb200_version(void) { return NLB200_VERSION; }
+
+const char* nlb200_status_string(int status) {
+  switch (status) {
+    case NLB200_OK: return "ok";
+    case NLB200_ERR_INVALID: return "invalid argument";
+    case NLB200_ERR_CUDA: return "CUDA error";
+    case NLB200_ERR_CAPACITY: return "partner-list capacity exceeded";
+    case NLB200_ERR_OUT_OF_BOX: return "particle outside the box";
+    case NLB200_ERR_ELL_ROWS: return "row longer than the ELL row capacity";
+    case NLB200_ERR_STATE: return "invalid call order";
+  }
+  return "unknown";
+}
+
+int nlb200_create(double search_length, double lx, double ly, double lz, int dtype, int mode, nlb200_handle* out) {
+  if (!out) return NLB200_ERR_INVALID;
+  *out = nullptr;
+  if (!(search_length > 0) || !(lx > 0) || !(ly > 0) || !(lz > 0)) return NLB200_ERR_INVALID;
+  if (dtype != NLB200_F32 && dtype != NLB200_F64) return NLB200_ERR_INVALID;
+  if (mode < NLB200_HALF_CSR || mode > NLB200_FULL_ELL_TRANSPOSED) return NLB200_ERR_INVALID;
+  nlb200_context* h = new (std::nothrow) nlb200_context();
+  if (!h) return NLB200_ERR_INVALID;
+  h->sl = search_length;
+  h->L[0] = lx;
+  h->L[1] = ly;
+  h->L[2] = lz;
+  h->dtype = dtype;
+  h->mode = mode;
+  const bool ok = (dtype == NLB200_F64) ? make_grid<double>(search_length, h->L, &h->gp64)
+                                        : make_grid<float>(search_length, h->L, &h->gp32);
+  if (!ok) {
+    // reference: mesh_size < 3 makes the wrapped stencil visit a cell twice (duplicate pairs), SURVEY.md §2b
+    delete h;
+    return NLB200_ERR_INVALID;
+  }
+  const int32_t* m = (dtype == NLB200_F64) ? h->gp64.mesh : h->gp32.mesh;
+  for (int d = 0; d < 3; d++) h->mesh[d] = m[d];
+  h->n_cells = (int64_t)m[0] * m[1] * m[2];
+  *out = h;
+  return NLB200_OK;
+}
+
+int nlb200_set_option(nlb200_handle h, int option, int64_t value) {
+  if (!h) return NLB200_ERR_INVALID;
+  if (h->initialized) return fail(h, NLB200_ERR_STATE, "options must be set before nlb200_initialize");
+  switch (option) {
+    case NLB200_OPT_POSITION_STRIDE:
+      if (value != 3 && value != 4) return fail(h, NLB200_ERR_INVALID, "position stride must be 3 or 4");
+      h->stride = (int)value;
+      return NLB200_OK;
+    case NLB200_OPT_SORT_ROWS: h->sort_rows = value != 0; return NLB200_OK;
+    case NLB200_OPT_ELL_ROWS:
+      if (value < 1 || value > 65536) return fail(h, NLB200_ERR_INVALID, "ell rows out of range");
+      h->ell_rows = (int)value;
+      return NLB200_OK;
+    case NLB200_OPT_EXACT_ONLY: h->exact_only = value != 0; return NLB200_OK;
+    case NLB200_OPT_USE_GRAPH: h->use_graph = value != 0; return NLB200_OK;
+    case NLB200_OPT_KERNEL_VARIANT: h->variant = (int)value; return NLB200_OK;
+    case NLB200_OPT_PROFILE: h->profile = value != 0; return NLB200_OK;
+  }
+  return fail(h, NLB200_ERR_INVALID, "unknown option %d", option);
+}
+
+int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entries) {
+  if (!h) return NLB200_ERR_INVALID;
+  if (max_particles < 0 || max_particles > 2147483647ll - 64)
+    return fail(h, NLB200_ERR_INVALID, "max_particles out of range (int32 ids)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(h, NLB200_ERR_CUDA, "no CUDA device: libnlist_b200 has no CPU fallback");
+  CK(h, cudaGetDevice(&h->device));
+  CK(h, set_search_attrs());
+  free_buffers(h);
+  const int64_t n = max_particles > 0 ? max_particles : 1;
+  const int64_t M = h->n_cells;
+  h->max_n = max_particles;
+  h->tiles_cells = (M + SCAN_TILE - 1) / SCAN_TILE + 1;
+  h->tiles_n = (n + SCAN_TILE - 1) / SCAN_TILE + 1;
+  // one zeroed region per build: histogram, both scans' look-back state, status block
+  size_t off = 0;
+  const size_t o_count = off;
+  off = align_up(off + sizeof(int32_t) * (size_t)(M + 1), 256);
+  const size_t o_sc = off;
+  off = align_up(off + sizeof(unsigned long long) * (size_t)(h->tiles_cells + 1), 256);
+  const size_t o_sn = off;
+  off = align_up(off + sizeof(unsigned long long) * (size_t)(h->tiles_n + 1), 256);
+  const size_t o_st = off;
+  off = align_up(off + sizeof(DeviceStatus), 256);
+  h->zero_bytes = off;
+  CK(h, cudaMalloc(&h->zero_region, off));
+  h->cell_count = reinterpret_cast<int32_t*>(h->zero_region + o_count);
+  h->scan_state_cells = reinterpret_cast<unsigned long long*>(h->zero_region + o_sc);
+  h->scan_state_counts = reinterpret_cast<unsigned long long*>(h->zero_region + o_sn);
+  h->status_dev = reinterpret_cast<DeviceStatus*>(h->zero_region + o_st);
+  CK(h, cudaMalloc(&h->cell_start, sizeof(int32_t) * (size_t)(M + 1)));
+  CK(h, cudaMalloc(&h->cell_rank, sizeof(int2) * (size_t)n));
+  CK(h, cudaMalloc(&h->perm, sizeof(int32_t) * (size_t)n));
+  CK(h, cudaMalloc(&h->sorted_ids, sizeof(int32_t) * (size_t)n));
+  CK(h, cudaMalloc(&h->rec, sizeof(float4) * (size_t)n));
+  CK(h, cudaMalloc(&h->counts, sizeof(int32_t) * (size_t)(n + 8)));
+  CK(h, cudaMalloc(&h->offsets, sizeof(int64_t) * (size_t)(n + 1)));
+  CK(h, cudaMalloc(&h->offsets32, sizeof(int32_t) * (size_t)(n + 1)));
+  CK(h, cudaMemset(h->offsets, 0, sizeof(int64_t) * (size_t)(n + 1)));
+  CK(h, cudaMemset(h->offsets32, 0, sizeof(int32_t) * (size_t)(n + 1)));
+  const int64_t entries = max_entries > 0 ? max_entries : estimate_entries(h, n);
+  int rc = alloc_partners(h, entries);
+  if (rc) return rc;
+  if (h->mode == NLB200_FULL_ELL_TRANSPOSED) {
+    // neighlist_gpu.hpp:102,271-274: MAX_PARTNERS * N ints, filled with -1 once
+    const int64_t tot = (int64_t)h->ell_rows * n;
+    CK(h, cudaMalloc(&h->ell, sizeof(int32_t) * (size_t)tot));
+    CK(h, cudaMalloc(&h->ell_prev, sizeof(int32_t) * (size_t)n));
+    h->ell_last_n = -1;  // first build fills it with -1
+  }
+  CK(h, cudaMallocHost(&h->status_host, sizeof(DeviceStatus)));
+  memset(h->status_host, 0, sizeof(DeviceStatus));
+  CK(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  if (h->profile)
+    for (int k = 0; k <= nlb200_context::MAX_STAGES; k++) CK(h, cudaEventCreate(&h->ev[k]));
+  CK(h, cudaDeviceSynchronize());
+  h->initialized = true;
+  h->have_result = false;
+  h->build_pending = false;
+  return NLB200_OK;
+}
+
+int nlb200_reserve(nlb200_handle h, int64_t max_entries) {
+  if (!h || !h->initialized) return h ? fail(h, NLB200_ERR_STATE, "reserve before initialize") : NLB200_ERR_INVALID;
+  if (max_entries <= h->cap_entries) return NLB200_OK;
+  if (h->build_pending) CK(h, cudaStreamSynchronize(h->last_stream));
+  drop_graph(h);
+  h->have_result = false;
+  return alloc_partners(h, max_entries);
+}
+
+int nlb200_destroy(nlb200_handle h) {
+  if (!h) return NLB200_OK;
+  if (h->build_pending && h->last_stream) cudaStreamSynchronize(h->last_stream);
+  free_buffers(h);
+  delete h;
+  return NLB200_OK;
+}
+
+int nlb200_build_subset(nlb200_handle h, const void* q_dev, int64_t n_total, int64_t n_owned,
+                        const int32_t* global_ids_dev, void* stream) {
+  if (!h) return NLB200_ERR_INVALID;
+  if (!h->initialized) return fail(h, NLB200_ERR_STATE, "build before initialize");
+  if (n_total < 0 || n_owned < 0 || n_owned > n_total || n_total > h->max_n)
+    return fail(h, NLB200_ERR_INVALID, "particle count %lld (owned %lld) outside [0, %lld]", (long long)n_total,
+                (long long)n_owned, (long long)h->max_n);
+  if (n_total > 0 && q_dev == nullptr) return fail(h, NLB200_ERR_INVALID, "null position pointer");
+  const size_t align = (h->stride == 4) ? 16 : (h->dtype == NLB200_F64 ? 8 : 4);
+  if ((reinterpret_cast<uintptr_t>(q_dev) % align) != 0)
+    return fail(h, NLB200_ERR_INVALID, "position pointer must be %zu-byte aligned", align);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int rc = NLB200_OK;
+  if (h->mode == NLB200_FULL_ELL_TRANSPOSED && n_owned != h->ell_last_n) {
+    // the view's row stride is the particle count (list[k*N + i], kernel_impl.cuh:30): a new N re-lays the matrix
+    // out, so start again from the reference's initial state (all -1, neighlist_gpu.hpp:271-274)
+    fill_i32_kernel<<<1024, 256, 0, s>>>(h->ell, (int64_t)h->ell_rows * (h->max_n > 0 ? h->max_n : 1), -1);
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemsetAsync(h->ell_prev, 0, sizeof(int32_t) * (size_t)(h->max_n > 0 ? h->max_n : 1), s));
+    h->ell_last_n = n_owned;
+  }
+  const bool can_graph = h->use_graph && !h->profile && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
+  if (can_graph) {
+    const bool hit = h->graph_exec && h->g_q == q_dev && h->g_n == n_total && h->g_owned == n_owned &&
+                     h->g_gids == global_ids_dev;
+    if (!hit) {
+      drop_graph(h);
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+      if (e == cudaSuccess) {
+        rc = enqueue_dispatch(h, q_dev, n_total, n_owned, global_ids_dev, s);
+        e = cudaStreamEndCapture(s, &graph);
+        if (rc == NLB200_OK && e == cudaSuccess && graph) {
+          e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+          if (e == cudaSuccess) {
+            h->g_q = q_dev;
+            h->g_n = n_total;
+            h->g_owned = n_owned;
+            h->g_gids = global_ids_dev;
+          } else {
+            h->graph_exec = nullptr;
+          }
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != NLB200_OK) return rc;
+      }
+      (void)cudaGetLastError();
+    }
+    if (h->graph_exec) {
+      CK(h, cudaGraphLaunch(h->graph_exec, s));
+    } else {
+      rc = enqueue_dispatch(h, q_dev, n_total, n_owned, global_ids_dev, s);
+    }
+  } else {
+    rc = enqueue_dispatch(h, q_dev, n_total, n_owned, global_ids_dev, s);
+  }
+  if (rc != NLB200_OK) return rc;
+  h->last_stream = s;
+  h->build_pending = true;
+  h->have_result = false;
+  h->last_n = n_total;
+  h->last_owned = n_owned;
+  return NLB200_OK;
+}
+
+int nlb200_build(nlb200_handle h, const void* q_dev, int64_t n, void* stream) {
+  return nlb200_build_subset(h, q_dev, n, n, nullptr, stream);
+}
+
+int nlb200_synchronize(nlb200_handle h) {
+  if (!h) return NLB200_ERR_INVALID;
+  if (!h->initialized) return fail(h, NLB200_ERR_STATE, "synchronize before initialize");
+  if (!h->build_pending && !h->have_result) return fail(h, NLB200_ERR_STATE, "no build to synchronize");
+  if (h->build_pending) {
+    CK(h, cudaStreamSynchronize(h->last_stream));
+    h->build_pending = false;
+  }
+  const DeviceStatus st = *h->status_host;
+  h->stats.n = h->last_owned;
+  h->stats.number_of_pairs = (int64_t)st.total_entries;
+  h->stats.candidates_tested = (int64_t)st.candidates;
+  h->stats.band_tests = (int64_t)st.band_tests;
+  h->stats.required_entries = (int64_t)st.total_entries;
+  h->stats.capacity_entries = h->cap_entries;
+  for (int d = 0; d < 3; d++) h->stats.mesh[d] = h->mesh[d];
+  h->stats.max_partners = st.max_partners;
+  h->stats.max_in_cell = st.max_in_cell;
+  h->have_result = true;
+  if (st.flags & FLAG_OUT_OF_BOX)
+    return fail(h, NLB200_ERR_OUT_OF_BOX, "a particle lies more than one cell outside [0,L] or is NaN");
+  if (st.flags & FLAG_CAPACITY)
+    return fail(h, NLB200_ERR_CAPACITY, "partner list needs %lld entries, capacity is %lld",
+                (long long)st.total_entries, (long long)h->cap_entries);
+  if (st.flags & FLAG_ELL_ROWS)
+    return fail(h, NLB200_ERR_ELL_ROWS, "a row has %d partners, ELL row capacity is %d", st.max_partners,
+                h->ell_rows);
+  return NLB200_OK;
+}
+
+int nlb200_build_host(nlb200_handle h, const void* q_host, int64_t n, int32_t* number_of_partners_host,
+                      int64_t* offsets_host, int32_t* partners_host, int64_t partners_capacity,
+                      int64_t* number_of_pairs) {
+  if (!h) return NLB200_ERR_INVALID;
+  if (!h->initialized) return fail(h, NLB200_ERR_STATE, "build before initialize");
+  if (n < 0 || n > h->max_n) return fail(h, NLB200_ERR_INVALID, "particle count out of range");
+  const size_t esz = h->dtype == NLB200_F64 ? 8 : 4;
+  const size_t bytes = (size_t)n * h->stride * esz;
+  if (!h->q_stage) CK(h, cudaMalloc(&h->q_stage, (size_t)(h->max_n > 0 ? h->max_n : 1) * h->stride * esz));
+  cudaStream_t s = h->own_stream;
+  if (bytes) CK(h, cudaMemcpyAsync(h->q_stage, q_host, bytes, cudaMemcpyHostToDevice, s));
+  int rc = nlb200_build(h, h->q_stage, n, s);
+  if (rc) return rc;
+  rc = nlb200_synchronize(h);
+  if (rc == NLB200_ERR_CAPACITY) {
+    // grow and retry once: the reference's answer to a full buffer is undefined behaviour
+    const int64_t need = h->stats.required_entries;
+    rc = nlb200_reserve(h, need + need / 16 + 1024);
+    if (rc) return rc;
+    rc = nlb200_build(h, h->q_stage, n, s);
+    if (rc) return rc;
+    rc = nlb200_synchronize(h);
+  }
+  if (rc) return rc;
+  const int64_t total = h->stats.number_of_pairs;
+  if (number_of_pairs) *number_of_pairs = total;
+  if (number_of_partners_host && n)
+    CK(h, cudaMemcpyAsync(number_of_partners_host, h->counts, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost,
+                          s));
+  if (offsets_host)
+    CK(h, cudaMemcpyAsync(offsets_host, h->offsets, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost, s));
+  if (partners_host) {
+    if (total > partners_capacity)
+      return fail(h, NLB200_ERR_CAPACITY, "host partner buffer holds %lld entries, %lld needed",
+                  (long long)partners_capacity, (long long)total);
+    if (total)
+      CK(h, cudaMemcpyAsync(partners_host, h->partners, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
+  }
+  CK(h, cudaStreamSynchronize(s));
+  return NLB200_OK;
+}
+
+const int32_t* nlb200_number_of_partners(nlb200_handle h) { return h ? h->counts : nullptr; }
+const int64_t* nlb200_offsets(nlb200_handle h) { return h ? h->offsets : nullptr; }
+const int32_t* nlb200_offsets32(nlb200_handle h) {
+  if (!h) return nullptr;
+  if (h->have_result && h->stats.number_of_pairs > 2147483647ll) return nullptr;
+  return h->offsets32;
+}
+const int32_t* nlb200_partners(nlb200_handle h) { return h ? h->partners : nullptr; }
+const int32_t* nlb200_ell_transposed(nlb200_handle h) { return h ? h->ell : nullptr; }
+const int32_t* nlb200_cell_start(nlb200_handle h) { return h ? h->cell_start : nullptr; }
+const int32_t* nlb200_sorted_ids(nlb200_handle h) { return h ? h->sorted_ids : nullptr; }
+
+int64_t nlb200_number_of_pairs(nlb200_handle h) {
+  if (!h || !h->have_result) return -1;
+  return h->stats.number_of_pairs;
+}
+
+int nlb200_get_stats(nlb200_handle h, nlb200_stats* out) {
+  if (!h || !out) return NLB200_ERR_INVALID;
+  if (!h->have_result) {
+    nlb200_stats s{};
+    for (int d = 0; d < 3; d++) s.mesh[d] = h->mesh[d];
+    s.capacity_entries = h->cap_entries;
+    *out = s;
+    return NLB200_OK;
+  }
+  *out = h->stats;
+  return NLB200_OK;
+}
+
+int nlb200_get_stage_times(nlb200_handle h, float* ms_out, int32_t* stage_ids_out, int capacity) {
+  if (!h || !h->profile || h->build_pending) return -1;
+  int k = 0;
+  for (; k < h->n_stages && k < capacity; k++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1]) != cudaSuccess) return -1;
+    ms_out[k] = ms;
+    stage_ids_out[k] = h->stage_id[k];
+  }
+  return k;
+}
+
+const char* nlb200_stage_name(int stage_id) {
+  return (stage_id >= 0 && stage_id < ST_NUM) ? kStageNames[stage_id] : "unknown";
+}
+
+int64_t nlb200_required_entries(nlb200_handle h) { return (h && h->have_result) ? h->stats.required_entries : -1; }
+
+const char* nlb200_last_error(nlb200_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+// ---- adjacent utilities ----------------------------------------------------------------------------------------
+
+int nlb200_select_slab(const void* q_dev, int64_t n, int dtype, int stride, int axis, double lo, double hi,
+                       int32_t* out_idx_dev, int64_t capacity, int64_t* out_count_dev, void* workspace_dev,
+                       int64_t workspace_bytes, void* stream) {
+  if (n < 0 || axis < 0 || axis > 2 || (stride != 3 && stride != 4)) return NLB200_ERR_INVALID;
+  // workspace: flags int32[n+8] | positions int64[n+1] | scan state u64[tiles+2]
+  const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE + 1;
+  const size_t o_flags = 0;
+  const size_t o_pos = align_up(sizeof(int32_t) * (size_t)(n + 8), 256);
+  const size_t o_state = align_up(o_pos + sizeof(int64_t) * (size_t)(n + 1), 256);
+  const size_t need = o_state + sizeof(unsigned long long) * (size_t)(tiles + 2);
+  if (workspace_dev == nullptr || (size_t)workspace_bytes < need) return NLB200_ERR_CAPACITY;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace_dev);
+  int32_t* flags = reinterpret_cast<int32_t*>(ws + o_flags);
+  int64_t* pos = reinterpret_cast<int64_t*>(ws + o_pos);
+  unsigned long long* state = reinterpret_cast<unsigned long long*>(ws + o_state);
+  if (cudaMemsetAsync(state, 0, sizeof(unsigned long long) * (size_t)(tiles + 2), s) != cudaSuccess)
+    return NLB200_ERR_CUDA;
+  const unsigned g = (unsigned)((n + 255) / 256);
+  if (n > 0) {
+    if (dtype == NLB200_F64)
+      slab_flag_kernel<double><<<g, 256, 0, s>>>((const double*)q_dev, n, stride, axis, lo, hi, flags);
+    else
+      slab_flag_kernel<float><<<g, 256, 0, s>>>((const float*)q_dev, n, stride, axis, lo, hi, flags);
+  }
+  scan_kernel<int64_t><<<(unsigned)(tiles - 1 > 0 ? tiles - 1 : 1), SCAN_THREADS, 0, s>>>(flags, n, pos, nullptr, state,
+                                                                                         nullptr, nullptr, 0);
+  slab_compact_kernel<<<g > 0 ? g : 1, 256, 0, s>>>(flags, pos, n, out_idx_dev, capacity, out_count_dev);
+  return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
+}
+
+int64_t nlb200_select_slab_workspace(int64_t n) {
+  const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE + 1;
+  const size_t o_pos = align_up(sizeof(int32_t) * (size_t)(n + 8), 256);
+  const size_t o_state = align_up(o_pos + sizeof(int64_t) * (size_t)(n + 1), 256);
+  return (int64_t)(o_state + sizeof(unsigned long long) * (size_t)(tiles + 2));
+}
+
+int nlb200_gather_records(const void* src_dev, const int32_t* idx_dev, int64_t count, int dtype, int stride,
+                          void* dst_dev, void* stream) {
+  if (count < 0 || (stride != 3 && stride != 4)) return NLB200_ERR_INVALID;
+  if (count == 0) return NLB200_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned g = (unsigned)((count * stride + 255) / 256);
+  if (dtype == NLB200_F64)
+    gather_records_kernel<double><<<g, 256, 0, s>>>((const double*)src_dev, idx_dev, count, stride, (double*)dst_dev);
+  else
+    gather_records_kernel<float><<<g, 256, 0, s>>>((const float*)src_dev, idx_dev, count, stride, (float*)dst_dev);
+  return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
+}
+
+}  // extern "C"

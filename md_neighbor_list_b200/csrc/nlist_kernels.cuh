@@ -1,0 +1,633 @@
+// nlist_kernels.cuh — hand-written sm_100a kernels of the Verlet-list build.
+//
+// Pipeline of one build (all on one stream, replayed as a CUDA graph):
+//   zero  -> bin_kernel        cell index + histogram            (reference: make_mesh, neighlist_gpu.hpp:26-41;
+//                                                                 MakeMeshidOfPtcl, neighlist_cpu.hpp:134-144)
+//         -> scan_kernel       exclusive scan of the histogram   (thrust::inclusive_scan, neighlist_gpu.hpp:173-175;
+//                                                                 MakeNextDest, neighlist_cpu.hpp:146-152)
+//         -> scatter_kernel    counting-sort scatter of ids      (thrust::sort_by_key, neighlist_gpu.hpp:190-199;
+//                                                                 neighlist_cpu.hpp:154-160)
+//         -> cellsort_kernel   ids ascending inside a cell + cell-sorted FP32 position records
+//                                                                (the SortPtclData / CopyGather the reference stubbed
+//                                                                 out: neighlist_cpu.hpp:176-180, neighlist_gpu.hpp:144-151)
+//         -> search_kernel<COUNT>  pair search, counts only      (kernel_impl.cuh:3-436, neighlist_cpu.hpp:239-359)
+//         -> scan_kernel       counts -> CSR offsets             (MakeNeighListForEachPtcl, neighlist_cpu.hpp:361-367)
+//         -> search_kernel<FILL>   pair search, emission into CSR (neighlist_cpu.hpp:369-372; replaces the
+//                                                                 row-major buffer + cublasSgeam transpose,
+//                                                                 kernel_impl.cuh:217-239)
+//         -> [sort_rows_kernel] [ell_kernel]
+//
+// Not a port: the reference searches with one thread/warp per particle gathering unsorted positions by id and writes
+// an ELL matrix.  Here positions are physically cell-sorted as 16-byte FP32 records relative to their cell corner,
+// a CTA stages the <= 9 contiguous x-runs of its stencil into shared memory in CTA-local coordinates, each thread
+// owns one i-particle and tests it against warp-broadcast j records with a 4-instruction FP32 dot-form pre-filter
+//   |xi-xj|^2 <= SL^2  <=>  xi.xj - |xj|^2/2 >= (|xi|^2 - SL^2)/2
+// whose rigorous error band (E) decides definite hit / definite miss; the few candidates inside the
+// band are re-tested exactly in the caller's precision with the reference's rounding order, so verdicts are
+// bit-identical to the reference while the hot loop runs on the FP32 pipe.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nlb {
+
+enum : uint32_t {
+  FLAG_OUT_OF_BOX = 1u,
+  FLAG_CAPACITY = 2u,
+  FLAG_ELL_ROWS = 4u,
+  FLAG_OFFSETS32 = 8u,  // total exceeds INT32_MAX: the int32 offsets view is invalid
+};
+
+// Device-resident status block, copied to pinned host memory at the end of every build.
+struct DeviceStatus {
+  unsigned long long total_entries;
+  unsigned long long candidates;
+  unsigned long long band_tests;
+  uint32_t flags;
+  int32_t max_partners;
+  int32_t max_in_cell;
+  int32_t pad;
+};
+
+template <typename T>
+struct GridParams {
+  int32_t mesh[3];
+  int32_t n_cells;
+  T ims[3];  // 1/ms, rounded as the reference does (neighlist_gpu.hpp:250-252)
+  T ms[3];   // cell edge (neighlist_gpu.hpp:246-248)
+  T sl2;     // SL*SL rounded once in T (neighlist_gpu.hpp:254)
+  float msf[3];
+  float sl2f;
+  float band;  // E: half-width of the FP32 pre-filter's uncertainty band in units of (SL2 - r2)/2
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+template <typename T>
+struct Vec3 {
+  T x, y, z;
+};
+
+// 128-bit vectorised loads of one AoS position record (Guideline 13).
+template <typename T, int STRIDE>
+__device__ __forceinline__ Vec3<T> load_pos(const T* __restrict__ q, int64_t i);
+
+template <>
+__device__ __forceinline__ Vec3<double> load_pos<double, 4>(const double* __restrict__ q, int64_t i) {
+  const double2* p = reinterpret_cast<const double2*>(q + 4 * i);
+  const double2 a = __ldg(p), b = __ldg(p + 1);
+  return {a.x, a.y, b.x};
+}
+template <>
+__device__ __forceinline__ Vec3<double> load_pos<double, 3>(const double* __restrict__ q, int64_t i) {
+  const double* p = q + 3 * i;
+  return {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+}
+template <>
+__device__ __forceinline__ Vec3<float> load_pos<float, 4>(const float* __restrict__ q, int64_t i) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(q + 4 * i));
+  return {a.x, a.y, a.z};
+}
+template <>
+__device__ __forceinline__ Vec3<float> load_pos<float, 3>(const float* __restrict__ q, int64_t i) {
+  const float* p = q + 3 * i;
+  return {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+}
+
+// The exact verdict in the caller's precision, with the rounding order nvcc/g++ give the reference expression
+// `drx*drx + dry*dry + drz*drz` (kernel_impl.cuh:25-29, neighlist_cpu.hpp:219-223): fma(dz,dz, fma(dy,dy, dx*dx)).
+// Explicit intrinsics so that no other contraction can be chosen by the compiler.
+__device__ __forceinline__ bool exact_within(const Vec3<double>& a, const Vec3<double>& b, double sl2) {
+  const double dx = __dsub_rn(a.x, b.x), dy = __dsub_rn(a.y, b.y), dz = __dsub_rn(a.z, b.z);
+  const double r2 = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
+  return !(r2 > sl2);
+}
+__device__ __forceinline__ bool exact_within(const Vec3<float>& a, const Vec3<float>& b, float sl2) {
+  const float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
+  const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+  return !(r2 > sl2);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 1. cell index + histogram
+// ---------------------------------------------------------------------------------------------------------------
+// idx = int(q * ims): the reference's reciprocal multiply + truncation (neighlist_gpu.hpp:31-35,
+// neighlist_cpu.hpp:52-56).  The reference GPU kernel clamps idx == mesh_size to mesh_size-1 and the CPU class wraps
+// one period; because distances are not periodic both give the same pair set for inputs in [0,L].
+// Here every index is clamped into [0, mesh-1], which additionally keeps particles slightly outside the box next to
+// their true neighbours; a particle more than one cell outside (or NaN) raises FLAG_OUT_OF_BOX because the FP32
+// pre-filter's error bound assumes |x - cell corner| <= 2 cells.
+template <typename T, int STRIDE>
+__global__ void __launch_bounds__(256) bin_kernel(const T* __restrict__ q, int32_t n, GridParams<T> gp,
+                                                  int32_t* __restrict__ cell_count, int2* __restrict__ cell_rank,
+                                                  DeviceStatus* __restrict__ st) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Vec3<T> p = load_pos<T, STRIDE>(q, i);
+  int32_t cx = static_cast<int32_t>(p.x * gp.ims[0]);
+  int32_t cy = static_cast<int32_t>(p.y * gp.ims[1]);
+  int32_t cz = static_cast<int32_t>(p.z * gp.ims[2]);
+  cx = min(max(cx, 0), gp.mesh[0] - 1);
+  cy = min(max(cy, 0), gp.mesh[1] - 1);
+  cz = min(max(cz, 0), gp.mesh[2] - 1);
+  const double rx = (double)p.x - (double)cx * (double)gp.ms[0];
+  const double ry = (double)p.y - (double)cy * (double)gp.ms[1];
+  const double rz = (double)p.z - (double)cz * (double)gp.ms[2];
+  const bool ok = (rx >= -(double)gp.ms[0]) && (rx <= 2.0 * (double)gp.ms[0]) && (ry >= -(double)gp.ms[1]) &&
+                  (ry <= 2.0 * (double)gp.ms[1]) && (rz >= -(double)gp.ms[2]) && (rz <= 2.0 * (double)gp.ms[2]);
+  if (!ok) atomicOr(&st->flags, FLAG_OUT_OF_BOX);
+  const int32_t cell = cx + (cy + cz * gp.mesh[1]) * gp.mesh[0];
+  const int32_t rank = atomicAdd(&cell_count[cell], 1);
+  cell_rank[i] = make_int2(cell, rank);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2. single-pass exclusive scan (decoupled look-back), int32 in -> TOut out, out has n+1 entries
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+// tile status word: bits 63..62 = state (0 invalid, 1 aggregate, 2 inclusive prefix), bits 61..0 = value
+constexpr unsigned long long SCAN_AGG = 1ull << 62;
+constexpr unsigned long long SCAN_PFX = 2ull << 62;
+constexpr unsigned long long SCAN_VAL = (1ull << 62) - 1;
+
+// `state` = [0]: dynamic tile counter, [1..]: tile status words; zeroed before launch.
+// If out32 != nullptr the same offsets are also written as int32 (the reference's key_pointer_ width).
+// If st != nullptr: the grand total goes to st->total_entries, the maximum input to *max_out, and FLAG_CAPACITY /
+// FLAG_OFFSETS32 are raised against `capacity`.
+template <typename TOut>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int32_t* __restrict__ in, int64_t n,
+                                                            TOut* __restrict__ out, int32_t* __restrict__ out32,
+                                                            unsigned long long* __restrict__ state,
+                                                            DeviceStatus* __restrict__ st, int32_t* max_out,
+                                                            long long capacity) {
+  __shared__ long long warp_sums[SCAN_THREADS / 32];
+  __shared__ long long tile_prefix_s;
+  __shared__ int tile_s;
+  __shared__ int warp_max[SCAN_THREADS / 32];
+  if (threadIdx.x == 0) tile_s = (int)atomicAdd(&state[0], 1ull);
+  __syncthreads();
+  const int tile = tile_s;
+  const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int32_t v[SCAN_ITEMS];
+  if (base + SCAN_ITEMS <= n && ((reinterpret_cast<uintptr_t>(in + base) & 15) == 0)) {
+    const int4 a = *reinterpret_cast<const int4*>(in + base);
+    const int4 b = *reinterpret_cast<const int4*>(in + base + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) v[k] = (base + k < n) ? in[base + k] : 0;
+  }
+  long long tsum = 0;
+  int tmax = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    tsum += v[k];
+    tmax = max(tmax, v[k]);
+  }
+  // block-wide inclusive scan of the per-thread sums
+  long long incl = tsum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const long long o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane_id() >= d) incl += o;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, d));
+  const int w = threadIdx.x >> 5;
+  if (lane_id() == 31) warp_sums[w] = incl;
+  if (lane_id() == 0) warp_max[w] = tmax;
+  __syncthreads();
+  long long wpre = 0, tile_total = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_THREADS / 32; k++) {
+    const long long s = warp_sums[k];
+    if (k < w) wpre += s;
+    tile_total += s;
+  }
+  // publish + look back (first warp)
+  if (w == 0) {
+    if (max_out != nullptr && lane_id() == 0) {
+      int m = 0;
+#pragma unroll
+      for (int k = 0; k < SCAN_THREADS / 32; k++) m = max(m, warp_max[k]);
+      if (m > 0) atomicMax(max_out, m);
+    }
+    long long prefix = 0;
+    if (tile == 0) {
+      if (lane_id() == 0) {
+        atomicExch(&state[1], SCAN_PFX | ((unsigned long long)tile_total & SCAN_VAL));
+      }
+    } else {
+      if (lane_id() == 0) {
+        atomicExch(&state[1 + tile], SCAN_AGG | ((unsigned long long)tile_total & SCAN_VAL));
+      }
+      int look = tile - 1;
+      while (true) {
+        const int idx = look - lane_id();
+        unsigned long long s = SCAN_PFX;  // lanes before tile 0 act as a zero prefix
+        if (idx >= 0) {
+          do {
+            s = *reinterpret_cast<volatile unsigned long long*>(&state[1 + idx]);
+          } while ((s >> 62) == 0);
+        }
+        const unsigned pfx_mask = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+        const int first_pfx = pfx_mask ? (__ffs(pfx_mask) - 1) : 32;
+        long long contrib = (lane_id() <= first_pfx) ? (long long)(s & SCAN_VAL) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+        prefix += contrib;
+        if (pfx_mask) break;
+        look -= 32;
+      }
+      if (lane_id() == 0) {
+        atomicExch(&state[1 + tile], SCAN_PFX | ((unsigned long long)(prefix + tile_total) & SCAN_VAL));
+      }
+    }
+    if (lane_id() == 0) tile_prefix_s = prefix;
+  }
+  __syncthreads();
+  long long run = tile_prefix_s + wpre + (incl - tsum);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) {
+      out[base + k] = (TOut)run;
+      if (out32 != nullptr) out32[base + k] = (int32_t)run;
+    }
+    run += v[k];
+  }
+  // the thread that owns the last element writes the grand total
+  if (n > 0 && base <= n - 1 && n - 1 < base + SCAN_ITEMS) {
+    out[n] = (TOut)run;
+    if (out32 != nullptr) out32[n] = (int32_t)run;
+    if (st != nullptr) {
+      st->total_entries = (unsigned long long)run;
+      uint32_t f = 0;
+      if (run > capacity) f |= FLAG_CAPACITY;
+      if (run > 2147483647ll) f |= FLAG_OFFSETS32;
+      if (f) atomicOr(&st->flags, f);
+    }
+  }
+  if (n == 0 && tile == 0 && threadIdx.x == 0) {
+    out[0] = (TOut)0;
+    if (out32 != nullptr) out32[0] = 0;
+    if (st != nullptr) st->total_entries = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3. counting-sort scatter of ids (arrival order inside a cell; made deterministic by cellsort_kernel)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) scatter_kernel(const int2* __restrict__ cell_rank, int32_t n,
+                                                      const int32_t* __restrict__ cell_start,
+                                                      int32_t* __restrict__ perm) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int2 cr = cell_rank[i];
+  perm[__ldg(cell_start + cr.x) + cr.y] = i;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 4. per-cell id sort (stable counting-sort order = ids ascending, neighlist_cpu.hpp:154-160) + physical reorder:
+//    rec[slot] = { float(x - cx*ms), float(y - cy*ms), float(z - cz*ms), id }   (cell-corner-relative FP32)
+//    One warp per cell; rank sort with warp shuffles (O(n^2/32) per cell, n ~ 35).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int STRIDE>
+__global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, GridParams<T> gp,
+                                                       const int32_t* __restrict__ cell_start,
+                                                       const int32_t* __restrict__ perm,
+                                                       int32_t* __restrict__ sorted_ids, float4* __restrict__ rec) {
+  const int32_t cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (cell >= gp.n_cells) return;
+  const int lane = lane_id();
+  const int32_t beg = __ldg(cell_start + cell);
+  const int32_t cnt = __ldg(cell_start + cell + 1) - beg;
+  if (cnt == 0) return;
+  const int32_t cx = cell % gp.mesh[0];
+  const int32_t cy = (cell / gp.mesh[0]) % gp.mesh[1];
+  const int32_t cz = cell / (gp.mesh[0] * gp.mesh[1]);
+  const double ox = (double)cx * (double)gp.ms[0], oy = (double)cy * (double)gp.ms[1],
+               oz = (double)cz * (double)gp.ms[2];
+  for (int32_t eb = 0; eb < cnt; eb += 32) {
+    const int32_t e = eb + lane;
+    const bool valid = e < cnt;
+    const int32_t id = valid ? __ldg(perm + beg + e) : 0x7fffffff;
+    int32_t rank = 0;
+    for (int32_t cb = 0; cb < cnt; cb += 32) {
+      const int32_t other = (cb + lane < cnt) ? __ldg(perm + beg + cb + lane) : 0x7fffffff;
+      const int lim = min(32, cnt - cb);
+      for (int t = 0; t < lim; t++) rank += (__shfl_sync(0xffffffffu, other, t) < id) ? 1 : 0;
+    }
+    if (valid) {
+      const Vec3<T> p = load_pos<T, STRIDE>(q, id);
+      float4 r;
+      r.x = (float)((double)p.x - ox);
+      r.y = (float)((double)p.y - oy);
+      r.z = (float)((double)p.z - oz);
+      r.w = __int_as_float(id);
+      sorted_ids[beg + rank] = id;
+      rec[beg + rank] = r;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 5/7. pair search.  One CTA per cell; thread t owns the t-th particle of the cell.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct SearchArgs {
+  const T* q;                 // caller's positions (exact re-test only)
+  GridParams<T> gp;
+  const int32_t* cell_start;  // [M+1]
+  const float4* rec;          // [n] cell-sorted records
+  const int32_t* global_ids;  // optional local -> global id map (multi-GPU), else nullptr
+  int32_t n_owned;            // rows are produced for local ids < n_owned
+  int32_t* counts;            // [n_owned]
+  const int64_t* offsets;     // [n_owned+1]   (FILL)
+  int32_t* partners;          // [capacity]    (FILL)
+  long long capacity;
+  DeviceStatus* st;
+  int32_t jt;                 // staged j records per shared-memory tile
+};
+
+// Stencil range along one axis: [c-1, c+1] clamped to the box.  The reference wraps the stencil periodically
+// (neighlist_gpu.hpp:125-142) but measures distances without minimum image, so a wrapped cell can only contribute
+// when it is also a direct neighbour, i.e. when the axis has exactly 3 cells — then all 3 cells are visited.
+__device__ __forceinline__ void axis_range(int c, int m, int& lo, int& hi) {
+  lo = max(c - 1, 0);
+  hi = min(c + 1, m - 1);
+  if (m == 3) {
+    lo = 0;
+    hi = 2;
+  }
+}
+
+template <typename T, int STRIDE, bool HALF, bool FILL, bool EXACT_ONLY>
+__global__ void __launch_bounds__(128) search_kernel(SearchArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* sj = reinterpret_cast<float4*>(smem_raw);
+  int32_t* sid = reinterpret_cast<int32_t*>(smem_raw + (size_t)a.jt * sizeof(float4));
+  __shared__ int32_t r_start[9], r_b1[9], r_b2[9], r_pre[10], r_dy[9], r_dz[9];
+  __shared__ int32_t s_xlo;
+
+  const GridParams<T>& gp = a.gp;
+  const int32_t cell = blockIdx.x;
+  const int32_t ibeg = __ldg(a.cell_start + cell);
+  const int32_t ni = __ldg(a.cell_start + cell + 1) - ibeg;
+  if (ni == 0) return;
+  if (FILL) {
+    // capacity overflow was detected by the offsets scan: emit nothing (status already flagged)
+    if (a.offsets[a.n_owned] > a.capacity) return;
+  }
+  const int32_t cx = cell % gp.mesh[0];
+  const int32_t cy = (cell / gp.mesh[0]) % gp.mesh[1];
+  const int32_t cz = cell / (gp.mesh[0] * gp.mesh[1]);
+
+  if (threadIdx.x == 0) {
+    int xlo, xhi, ylo, yhi, zlo, zhi;
+    axis_range(cx, gp.mesh[0], xlo, xhi);
+    axis_range(cy, gp.mesh[1], ylo, yhi);
+    axis_range(cz, gp.mesh[2], zlo, zhi);
+    s_xlo = xlo;
+    int r = 0, pre = 0;
+    for (int z = zlo; z <= zhi; z++)
+      for (int y = ylo; y <= yhi; y++) {
+        const int32_t row = (y + z * gp.mesh[1]) * gp.mesh[0];
+        const int32_t s0 = a.cell_start[row + xlo];
+        const int32_t s3 = a.cell_start[row + xhi + 1];
+        r_start[r] = s0;
+        r_b1[r] = (xlo + 1 <= xhi) ? a.cell_start[row + xlo + 1] : 0x7fffffff;
+        r_b2[r] = (xlo + 2 <= xhi) ? a.cell_start[row + xlo + 2] : 0x7fffffff;
+        r_dy[r] = y - cy;
+        r_dz[r] = z - cz;
+        r_pre[r] = pre;
+        pre += s3 - s0;
+        r++;
+      }
+    for (; r < 9; r++) {
+      r_start[r] = 0;
+      r_b1[r] = r_b2[r] = 0x7fffffff;
+      r_dy[r] = r_dz[r] = 0;
+      r_pre[r] = pre;
+    }
+    r_pre[9] = pre;
+  }
+  __syncthreads();
+  const int32_t nj = r_pre[9];
+  const int32_t xlo = s_xlo;
+  const float hx = 0.5f * gp.msf[0], hy = 0.5f * gp.msf[1], hz = 0.5f * gp.msf[2];
+
+  unsigned long long band_local = 0;
+
+  for (int32_t ib = 0; ib < ni; ib += blockDim.x) {
+    // ---- this thread's i particle ----
+    const int32_t il = ib + threadIdx.x;
+    bool active = il < ni;
+    float xi = 0.f, yi = 0.f, zi = 0.f;
+    int32_t iid = -1;
+    if (active) {
+      const float4 r = __ldg(a.rec + ibeg + il);
+      xi = r.x - hx;
+      yi = r.y - hy;
+      zi = r.z - hz;
+      iid = __float_as_int(r.w);
+      active = iid < a.n_owned;
+    }
+    const int32_t icmp = (a.global_ids != nullptr && iid >= 0) ? __ldg(a.global_ids + iid) : iid;
+    const float ai = 0.5f * (fmaf(xi, xi, fmaf(yi, yi, zi * zi)) - gp.sl2f);
+    const float a_lo = active ? (ai - gp.band) : __int_as_float(0x7f800000);  // +inf: never hits
+    const float a_hi = ai + gp.band;
+    Vec3<T> qi_exact = {0, 0, 0};
+    if (EXACT_ONLY && active) qi_exact = load_pos<T, STRIDE>(a.q, iid);
+
+    int32_t cnt = 0;
+    int32_t* wptr = nullptr;
+    if (FILL && active) wptr = a.partners + a.offsets[iid];
+
+    for (int32_t jb = 0; jb < nj; jb += a.jt) {
+      const int32_t jn = min(a.jt, nj - jb);
+      __syncthreads();  // previous tile fully consumed
+      // ---- stage j records of this tile in CTA-local coordinates (origin = centre of the i cell) ----
+      for (int32_t k = threadIdx.x; k < jn; k += blockDim.x) {
+        const int32_t g = jb + k;
+        int r = 0;
+#pragma unroll
+        for (int t = 1; t < 9; t++) r += (g >= r_pre[t]) ? 1 : 0;
+        const int32_t slot = r_start[r] + (g - r_pre[r]);
+        const int32_t dxc = xlo + ((slot >= r_b1[r]) ? 1 : 0) + ((slot >= r_b2[r]) ? 1 : 0) - cx;
+        const float4 rj = __ldg(a.rec + slot);
+        const float x = fmaf((float)dxc - 0.5f, gp.msf[0], rj.x);
+        const float y = fmaf((float)r_dy[r] - 0.5f, gp.msf[1], rj.y);
+        const float z = fmaf((float)r_dz[r] - 0.5f, gp.msf[2], rj.z);
+        const float nb = -0.5f * fmaf(x, x, fmaf(y, y, z * z));
+        sj[k] = make_float4(x, y, z, nb);
+        sid[k] = __float_as_int(rj.w);
+      }
+      __syncthreads();
+      // ---- test ----
+#pragma unroll 4
+      for (int32_t k = 0; k < jn; k++) {
+        const float4 j = sj[k];
+        const float t = fmaf(xi, j.x, fmaf(yi, j.y, fmaf(zi, j.z, j.w)));
+        bool hit = EXACT_ONLY ? active : (t >= a_lo);
+        if (hit) {
+          const int32_t jid = sid[k];
+          if (EXACT_ONLY) {
+            hit = exact_within(qi_exact, load_pos<T, STRIDE>(a.q, jid), gp.sl2);
+          } else if (t < a_hi) {
+            // inside the pre-filter's uncertainty band: decide exactly, in the caller's precision
+            hit = exact_within(load_pos<T, STRIDE>(a.q, iid), load_pos<T, STRIDE>(a.q, jid), gp.sl2);
+            band_local++;
+          }
+          const int32_t jcmp = (a.global_ids != nullptr) ? __ldg(a.global_ids + jid) : jid;
+          hit = hit && (HALF ? (jcmp > icmp) : (jid != iid));
+          if (hit) {
+            if (FILL) *wptr++ = jcmp;
+            cnt++;
+          }
+        }
+      }
+    }
+    if (!FILL && il < ni && iid >= 0 && iid < a.n_owned) a.counts[iid] = cnt;
+  }
+  if (!FILL) {
+    if (threadIdx.x == 0) atomicAdd(&a.st->candidates, (unsigned long long)ni * (unsigned long long)nj);
+    if (band_local) atomicAdd(&a.st->band_tests, band_local);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 8. optional: rows ascending (what the reference tests do on the host before comparing, make_list.cpp:120-128).
+//    One warp per row; bitonic sort in shared memory for rows <= SORT_SMEM, in global memory beyond.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SORT_SMEM = 1024;
+constexpr int SORT_WARPS = 4;
+
+// Ascending-only bitonic network ("flip" formulation): every comparator leaves the minimum at the lower index, so a
+// virtual +inf padding above `len` never moves and comparators that touch it can simply be skipped — any length
+// works in place, in shared or global memory.
+__device__ __forceinline__ void bitonic_warp(int32_t* buf, int len, int lane) {
+  int p2 = 1;
+  while (p2 < len) p2 <<= 1;
+  for (int k = 2; k <= p2; k <<= 1) {
+    for (int t = lane; t < len; t += 32) {
+      const int p = t ^ (k - 1);
+      if (p > t && p < len) {
+        const int32_t x = buf[t], y = buf[p];
+        if (x > y) {
+          buf[t] = y;
+          buf[p] = x;
+        }
+      }
+    }
+    __syncwarp();
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      for (int t = lane; t < len; t += 32) {
+        const int p = t ^ j;
+        if (p > t && p < len) {
+          const int32_t x = buf[t], y = buf[p];
+          if (x > y) {
+            buf[t] = y;
+            buf[p] = x;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SORT_WARPS * 32) sort_rows_kernel(const int64_t* __restrict__ offsets,
+                                                                    int32_t n_rows, int32_t* partners,
+                                                                    long long capacity) {
+  __shared__ int32_t sbuf[SORT_WARPS][SORT_SMEM];
+  if (offsets[n_rows] > capacity) return;
+  const int lane = lane_id();
+  const int w = threadIdx.x >> 5;
+  const int32_t row = blockIdx.x * SORT_WARPS + w;
+  if (row >= n_rows) return;
+  const int64_t beg = offsets[row];
+  const int32_t len = (int32_t)(offsets[row + 1] - beg);
+  if (len <= 1) return;
+  int32_t* g = partners + beg;
+  if (len <= SORT_SMEM) {
+    int32_t* buf = sbuf[w];
+    for (int t = lane; t < len; t += 32) buf[t] = g[t];
+    __syncwarp();
+    bitonic_warp(buf, len, lane);
+    for (int t = lane; t < len; t += 32) g[t] = buf[t];
+  } else {
+    // rows this long only occur in the clustered stress configuration: same network, in place in global memory
+    // (__syncwarp orders the lanes' global accesses between stages)
+    bitonic_warp(g, len, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 9. optional: the reference GPU layout list[k*n + i], -1 padded (kernel_impl.cuh:30, neighlist_gpu.hpp:271-274)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ell_kernel(const int64_t* __restrict__ offsets,
+                                                  const int32_t* __restrict__ partners, int32_t n, int32_t rows,
+                                                  int32_t* __restrict__ ell, int32_t* __restrict__ prev_count,
+                                                  long long capacity, DeviceStatus* st) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (offsets[n] > capacity) return;
+  const int64_t beg = offsets[i];
+  int32_t cnt = (int32_t)(offsets[i + 1] - beg);
+  if (cnt > rows) {
+    atomicOr(&st->flags, FLAG_ELL_ROWS);
+    cnt = rows;
+  }
+  for (int32_t k = 0; k < cnt; k++) ell[(int64_t)k * n + i] = partners[beg + k];
+  const int32_t prev = prev_count[i];
+  for (int32_t k = cnt; k < prev; k++) ell[(int64_t)k * n + i] = -1;
+  prev_count[i] = cnt;
+}
+
+__global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// adjacent utilities: slab selection (deterministic, ascending) and record gather for the halo exchange
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) slab_flag_kernel(const T* __restrict__ q, int64_t n, int stride, int axis,
+                                                        double lo, double hi, int32_t* __restrict__ flags) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = (double)q[i * stride + axis];
+  flags[i] = (v >= lo && v < hi) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) slab_compact_kernel(const int32_t* __restrict__ flags,
+                                                           const int64_t* __restrict__ pos, int64_t n,
+                                                           int32_t* __restrict__ out, int64_t capacity,
+                                                           int64_t* __restrict__ out_count) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i == 0) *out_count = pos[n];
+  if (i >= n) return;
+  if (flags[i] && pos[i] < capacity) out[pos[i]] = (int32_t)i;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gather_records_kernel(const T* __restrict__ src,
+                                                             const int32_t* __restrict__ idx, int64_t count,
+                                                             int stride, T* __restrict__ dst) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= count * stride) return;
+  const int64_t k = t / stride;
+  const int c = (int)(t - k * stride);
+  dst[t] = src[(int64_t)idx[k] * stride + c];
+}
+
+}  // namespace nlb

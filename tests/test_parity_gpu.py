@@ -1,0 +1,423 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libnlist_b200.so), against the oracle on the
+same seeded inputs, against the golden fixtures recorded from the reference, and — at full size — through
+size-independent properties.  Integer/index outputs must be bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+BOX50 = (50.0, 50.0, 50.0)
+
+
+def gpu_build(torch, q, sl, box, mode, dtype="f64", builds=1, max_entries=0, **opts):
+    """Run the product on `q` (numpy (n, stride)); returns dict of numpy outputs (rows NOT sorted) + stats."""
+    from md_neighbor_list_b200 import VerletListB200
+    stride = q.shape[1]
+    nl = VerletListB200(sl, box[0], box[1], box[2], dtype=dtype, mode=mode, position_stride=stride, **opts)
+    nl.initialize(max(q.shape[0], 1), max_entries)
+    qd = torch.from_numpy(np.ascontiguousarray(q)).cuda()
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        for _ in range(builds):
+            nl.build(qd)
+    from md_neighbor_list_b200 import NlistError, _lib
+    try:
+        st = nl.synchronize()
+    except NlistError as e:
+        if e.status != _lib.ERR_CAPACITY:
+            raise
+        nl.reserve(nl.stats().required_entries)
+        with torch.cuda.stream(stream):
+            nl.build(qd)
+        st = nl.synchronize()
+    out = {
+        "np": nl.number_of_partners().cpu().numpy().copy(),
+        "off": nl.offsets().cpu().numpy().copy(),
+        "list": nl.partners().cpu().numpy().copy(),
+        "cell_start": nl.cell_start().cpu().numpy().copy(),
+        "sorted_ids": nl.sorted_ids(q.shape[0]).cpu().numpy().copy(),
+        "pairs": st.number_of_pairs, "candidates": st.candidates_tested, "band": st.band_tests,
+        "max_partners": st.max_partners, "max_in_cell": st.max_in_cell, "handle": nl,
+    }
+    return out
+
+
+def sort_rows(oracle, lst, off):
+    out = lst.copy()
+    oracle.lib().orc_sort_rows(out.ctypes.data, off.ctypes.data, len(off) - 1)
+    return out
+
+
+def assert_matches(oracle, got, ref):
+    """ref: oracle CSR (any row order).  Bit-exact after the per-row sort the reference tests apply
+    (make_list.cpp:120-128,205-220)."""
+    refs = ref.sorted_rows()
+    assert got["pairs"] == refs.number_of_pairs
+    assert np.array_equal(got["np"], refs.number_of_partners)
+    assert np.array_equal(got["off"], refs.offsets)
+    assert np.array_equal(sort_rows(oracle, got["list"], got["off"]), refs.partners)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference's default systems (BASELINE.json configs[0] and configs[1])
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dens", [0.5, 1.0])
+def test_default_system_half_matches_reference_fingerprints(cuda, oracle, dens):
+    """configs[0]/[1]: bit-exact against the fingerprints of the reference's CPU classes (scalar, AVX2 4x1,
+    AVX-512 8x1 all agree; tests/golden/make_golden.py) and against the oracle."""
+    from md_neighbor_list_b200 import workloads
+    with open(os.path.join(GOLD, "default_systems.json")) as f:
+        g = json.load(f)[f"density_{dens}"]
+    q = workloads.fcc(dens)
+    assert oracle.fnv1a64(q[:, :3]) == g["positions_xyz_fnv"]
+    got = gpu_build(cuda, q, 3.3, BOX50, "half_csr")
+    assert got["pairs"] == g["half"]["number_of_pairs"]
+    assert oracle.fnv1a64(got["np"]) == g["half"]["number_of_partners_fnv"]
+    assert oracle.fnv1a64(got["off"].astype(np.int32)) == g["half"]["key_pointer_i32_fnv"]
+    assert oracle.fnv1a64(sort_rows(oracle, got["list"], got["off"])) == g["half"]["sorted_list_rowsorted_fnv"]
+    assert got["max_partners"] == g["half"]["max_partners"]
+    assert_matches(oracle, got, oracle.build_half(q, 3.3, BOX50))
+    # 32-bit offsets view = the reference's key_pointer_ type
+    off32 = got["handle"].offsets32().cpu().numpy()
+    assert np.array_equal(off32.astype(np.int64), got["off"])
+
+
+@pytest.mark.parametrize("dens", [0.5, 1.0])
+def test_default_system_full_matches_oracle(cuda, oracle, dens):
+    from md_neighbor_list_b200 import workloads
+    with open(os.path.join(GOLD, "default_systems.json")) as f:
+        g = json.load(f)[f"density_{dens}"]
+    q = workloads.fcc(dens)
+    got = gpu_build(cuda, q, 3.3, BOX50, "full_csr", builds=3)
+    assert got["pairs"] == g["full"]["number_of_pairs"]
+    assert got["candidates"] == g["full"]["candidates_27"] or got["candidates"] <= g["full"]["candidates_27"]
+    assert oracle.fnv1a64(sort_rows(oracle, got["list"], got["off"])) == g["full"]["list_rowsorted_fnv"]
+    assert oracle.fnv1a64(got["off"]) == g["full"]["offsets_i64_fnv"]
+    assert got["max_partners"] == g["full"]["max_partners"]
+    ref = oracle.build_full(q, 3.3, BOX50)
+    assert_matches(oracle, got, ref)
+    # cell binning parity: mesh_index_ and ptcl_id_in_mesh_ (neighlist_cpu.hpp:146-165)
+    mi, pid, _ = oracle.bin_particles(q, 3.3, BOX50, gpu_clamp=True)
+    assert np.array_equal(got["cell_start"].astype(np.int64), mi)
+    assert np.array_equal(got["sorted_ids"], pid)
+    assert got["max_in_cell"] == int(np.diff(mi).max())
+    # stencil order (default): rows come out exactly in the oracle's discovery order, not merely as equal sets
+    assert np.array_equal(got["list"], ref.partners)
+
+
+def test_small_golden_fixture(cuda, oracle):
+    z = np.load(os.path.join(GOLD, "small_mesh3.npz"))
+    q, L, SL = z["q"], float(z["L"]), float(z["SL"])
+    got = gpu_build(cuda, q, SL, (L, L, L), "half_csr")
+    assert np.array_equal(got["np"], z["half_np"]) and np.array_equal(got["off"], z["half_off"])
+    assert np.array_equal(sort_rows(oracle, got["list"], got["off"]), z["half_list"])
+    got = gpu_build(cuda, q, SL, (L, L, L), "full_csr")
+    assert np.array_equal(got["np"], z["full_np"]) and np.array_equal(got["off"], z["full_off"])
+    assert np.array_equal(sort_rows(oracle, got["list"], got["off"]), z["full_list"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# precision / layout variants
+# ---------------------------------------------------------------------------------------------------------------
+def test_float32_positions(cuda, oracle):
+    """The reference's float toggle (make_list.cu:6-12): verdicts computed in FP32 exactly as the reference does."""
+    from md_neighbor_list_b200 import workloads
+    q = workloads.fcc(1.0, 30.0).astype(np.float32)
+    box = (30.0, 30.0, 30.0)
+    got = gpu_build(cuda, q, 3.3, box, "full_csr", dtype="f32")
+    assert_matches(oracle, got, oracle.build_full(q, 3.3, box))
+    got = gpu_build(cuda, q, 3.3, box, "half_csr", dtype="f32")
+    assert_matches(oracle, got, oracle.build_half(q, 3.3, box))
+
+
+def test_xyz_stride3(cuda, oracle):
+    """The scalar CPU Vec has three doubles (make_list.cpp:30)."""
+    from md_neighbor_list_b200 import workloads
+    q = workloads.fcc(0.5, 25.0, stride=3)
+    box = (25.0, 25.0, 25.0)
+    got = gpu_build(cuda, q, 3.3, box, "half_csr")
+    assert_matches(oracle, got, oracle.build_half(q, 3.3, box))
+    qf = q.astype(np.float32)
+    got = gpu_build(cuda, qf, 3.3, box, "full_csr", dtype="f32")
+    assert_matches(oracle, got, oracle.build_full(qf, 3.3, box))
+
+
+def test_exact_only_equals_prefilter(cuda, oracle):
+    rng = np.random.default_rng(5)
+    q = np.zeros((6000, 4))
+    q[:, :3] = rng.random((6000, 3)) * 21.0
+    box = (21.0, 21.0, 21.0)
+    a = gpu_build(cuda, q, 3.0, box, "full_csr")
+    b = gpu_build(cuda, q, 3.0, box, "full_csr", exact_only=True)
+    assert np.array_equal(a["off"], b["off"]) and np.array_equal(a["list"], b["list"])
+    assert_matches(oracle, a, oracle.build_full(q, 3.0, box))
+
+
+def test_pairs_on_the_search_radius_take_the_exact_path(cuda, oracle):
+    """Adversarial: partners placed within a few ulp of SL (both sides).  The FP32 pre-filter cannot decide these;
+    the exact FP64 re-test must reproduce the reference verdict, and the band counter must see them."""
+    rng = np.random.default_rng(11)
+    SL, L = 3.3, 40.0
+    n0 = 4000
+    base = rng.random((n0, 3)) * (L - 8.0) + 4.0
+    dirs = rng.normal(size=(n0, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    scale = SL * (1.0 + rng.integers(-4, 5, size=(n0, 1)) * 2.0 ** -52)
+    q = np.zeros((2 * n0, 4))
+    q[:n0, :3] = base
+    q[n0:, :3] = base + dirs * scale
+    box = (L, L, L)
+    got = gpu_build(cuda, q, SL, box, "full_csr")
+    assert got["band"] >= n0  # every constructed pair is inside the band (seen from both sides)
+    assert_matches(oracle, got, oracle.build_full(q, SL, box))
+    bf = oracle.bruteforce(q, SL, full=True)
+    assert np.array_equal(sort_rows(oracle, got["list"], got["off"]), bf.partners)
+    rep = oracle.band_report(q, SL, box, cap=10000)
+    # reported separately, as north_star asks: pairs whose verdict depends on the rounding order
+    assert rep["within_1ulp"] >= 0 and rep["order_dependent"] >= 0
+    # float32 too
+    qf = q.astype(np.float32)
+    got = gpu_build(cuda, qf, SL, box, "full_csr", dtype="f32")
+    assert_matches(oracle, got, oracle.build_full(qf, SL, box))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------------------------
+def test_empty_and_tiny_inputs(cuda, oracle):
+    box = (20.0, 20.0, 20.0)
+    for mode in ("half_csr", "full_csr"):
+        got = gpu_build(cuda, np.zeros((0, 4)), 3.3, box, mode)
+        assert got["pairs"] == 0 and list(got["off"]) == [0]
+        got = gpu_build(cuda, np.array([[1.0, 2.0, 3.0, 0.0]]), 3.3, box, mode)
+        assert got["pairs"] == 0 and list(got["np"]) == [0]
+    q = np.array([[1.0, 1.0, 1.0, 0], [1.0, 1.0, 4.3, 0], [1.0, 1.0, 4.3000001, 0], [19.9, 19.9, 19.9, 0]])
+    got = gpu_build(cuda, q, 3.3, box, "full_csr")
+    assert_matches(oracle, got, oracle.bruteforce(q, 3.3, full=True))
+    got = gpu_build(cuda, q, 3.3, box, "half_csr")
+    assert_matches(oracle, got, oracle.bruteforce(q, 3.3, full=False))
+
+
+def test_sparse_box_with_empty_cells(cuda, oracle):
+    """The reference GPU path breaks when a cell is empty (reduce_by_key); this one must not."""
+    rng = np.random.default_rng(3)
+    q = np.zeros((300, 4))
+    q[:, :3] = rng.random((300, 3)) * 60.0
+    box = (60.0, 60.0, 60.0)
+    got = gpu_build(cuda, q, 3.3, box, "full_csr")
+    assert_matches(oracle, got, oracle.bruteforce(q, 3.3, full=True))
+    assert (np.diff(got["cell_start"]) == 0).sum() > 1000
+
+
+def test_ragged_non_cubic_and_boundary_particles(cuda, oracle):
+    rng = np.random.default_rng(8)
+    box = (13.0, 29.5, 10.1)  # 3 / 8 / 3 cells: wrapped stencil cells are real neighbours on the 3-cell axes
+    n = 5000
+    q = np.zeros((n, 4))
+    q[:, :3] = rng.random((n, 3)) * np.array(box)
+    q[:50, 0] = 0.0
+    q[50:100, 1] = box[1]          # exactly on the upper wall (reference GPU kernel clamps idx == mesh)
+    q[100:150, 2] = np.nextafter(box[2], 0)
+    q[150:170, :3] = q[170:190, :3]  # duplicates: r2 == 0
+    for mode, full in (("full_csr", True), ("half_csr", False)):
+        got = gpu_build(cuda, q, 3.3, box, mode)
+        assert_matches(oracle, got, oracle.bruteforce(q, 3.3, full=full))
+
+
+def test_clustered_heavy_cells(cuda, oracle):
+    from md_neighbor_list_b200 import workloads
+    q = workloads.clustered(12000, 30.0, blobs=4)
+    box = (30.0, 30.0, 30.0)
+    got = gpu_build(cuda, q, 2.3, box, "full_csr")
+    assert got["max_in_cell"] > 128  # exercises multi-batch i loops and multi-tile staging
+    assert_matches(oracle, got, oracle.build_full(q, 2.3, box))
+    got = gpu_build(cuda, q, 2.3, box, "half_csr")
+    assert_matches(oracle, got, oracle.build_half(q, 2.3, box))
+
+
+def test_out_of_box_and_nan_are_reported(cuda):
+    from md_neighbor_list_b200 import NlistError, VerletListB200, _lib
+    torch = cuda
+    for bad in (500.0, float("nan"), -40.0):
+        q = np.random.default_rng(0).random((1000, 4)) * 20.0
+        q[17, 1] = bad
+        nl = VerletListB200(3.3, 20.0, 20.0, 20.0)
+        nl.initialize(1000)
+        nl.build(torch.from_numpy(q).cuda())
+        with pytest.raises(NlistError) as e:
+            nl.synchronize()
+        assert e.value.status == _lib.ERR_OUT_OF_BOX
+
+
+def test_slightly_outside_the_box_is_still_exact(cuda, oracle):
+    """Up to one cell outside [0,L] the clamp keeps particles next to their neighbours; result = brute force."""
+    rng = np.random.default_rng(2)
+    q = np.zeros((3000, 4))
+    q[:, :3] = rng.random((3000, 3)) * 22.0 - 1.0  # [-1, 21] in a 20-box
+    box = (20.0, 20.0, 20.0)
+    got = gpu_build(cuda, q, 3.3, box, "full_csr")
+    assert_matches(oracle, got, oracle.bruteforce(q, 3.3, full=True))
+
+
+def test_capacity_overflow_is_detected_then_recovered(cuda, oracle):
+    from md_neighbor_list_b200 import NlistError, VerletListB200, _lib, workloads
+    torch = cuda
+    q = workloads.fcc(1.0, 20.0)
+    qd = torch.from_numpy(q).cuda()
+    nl = VerletListB200(3.3, 20.0, 20.0, 20.0, mode="full_csr")
+    nl.initialize(q.shape[0], max_entries=1000)  # far too small
+    nl.build(qd)
+    with pytest.raises(NlistError) as e:
+        nl.synchronize()
+    assert e.value.status == _lib.ERR_CAPACITY
+    need = nl.stats().required_entries
+    ref = oracle.build_full(q, 3.3, (20.0, 20.0, 20.0))
+    assert need == ref.number_of_pairs
+    nl.reserve(need)
+    nl.build(qd)
+    st = nl.synchronize()
+    assert st.number_of_pairs == need
+    got = {"np": nl.number_of_partners().cpu().numpy(), "off": nl.offsets().cpu().numpy(),
+           "list": nl.partners().cpu().numpy(), "pairs": st.number_of_pairs}
+    assert_matches(oracle, got, ref)
+
+
+def test_rows_sorted_on_device(cuda, oracle):
+    from md_neighbor_list_b200 import workloads
+    q = workloads.fcc(1.0, 25.0)
+    box = (25.0, 25.0, 25.0)
+    got = gpu_build(cuda, q, 3.3, box, "full_csr", sort_rows=True)
+    ref = oracle.build_full(q, 3.3, box).sorted_rows()
+    assert np.array_equal(got["off"], ref.offsets)
+    assert np.array_equal(got["list"], ref.partners)  # no host-side sort
+
+
+def test_ell_transposed_reference_layout(cuda, oracle):
+    """NeighListGPU mirror: neigh_list()[k*N + i], -1 padded, MAX_PARTNERS rows (kernel_impl.cuh:30;
+    make_list.cu:156-198 reads it exactly like this)."""
+    from md_neighbor_list_b200 import NeighListGPU, workloads
+    torch = cuda
+    L = 25.0
+    q = workloads.fcc(1.0, L)
+    n = q.shape[0]
+    nl = NeighListGPU(3.3, L, L, L)
+    nl.Initialize(n)
+    qd = torch.from_numpy(q).cuda()
+    nl.MakeNeighList(qd, n, sync=False)
+    total = nl.number_of_pairs()
+    ref = oracle.build_full(q, 3.3, (L, L, L))
+    assert total == ref.number_of_pairs
+    ell = nl.neigh_list().cpu().numpy()
+    cnt = nl.number_of_partners().cpu().numpy()
+    assert np.array_equal(cnt, ref.number_of_partners)
+    ref_ell = oracle.ell_from_csr(ref, NeighListGPU.MAX_PARTNERS)
+    assert np.array_equal(ell, ref_ell)  # same stencil order as the oracle, so equal without sorting
+    # rebuild with fewer particles: rows beyond the new counts must be -1 again (the reference leaves stale entries)
+    m = n // 2
+    nl.MakeNeighList(qd, m, sync=True)
+    ref2 = oracle.build_full(q[:m], 3.3, (L, L, L))
+    ell2 = nl.neigh_list().cpu().numpy()
+    assert np.array_equal(ell2, oracle.ell_from_csr(ref2, NeighListGPU.MAX_PARTNERS))
+
+
+def test_cpu_class_mirror_host_buffers(cuda, oracle):
+    """NeighList mirror (make_list.cpp:143-163): host arrays in, half CSR out, checked the way the reference driver
+    checks itself (make_list.cpp:183-222)."""
+    from md_neighbor_list_b200 import NeighList, workloads
+    L = 25.0
+    q = workloads.fcc(0.5, L)
+    n = q.shape[0]
+    nlist = NeighList(3.3, L, L, L)
+    nlist.Initialize(n)
+    nlist.MakeNeighList(q, n)
+    ref = oracle.bruteforce(q, 3.3, full=False)
+    assert nlist.number_of_pairs() == ref.number_of_pairs
+    assert np.array_equal(nlist.number_of_partners(), ref.number_of_partners)
+    kp = nlist.key_pointer()
+    assert kp.dtype == np.int32 and np.array_equal(kp.astype(np.int64), ref.offsets)
+    assert np.array_equal(sort_rows(oracle, nlist.sorted_list(), ref.offsets), ref.partners)
+
+
+def test_deterministic_across_builds_and_graph_replay(cuda):
+    from md_neighbor_list_b200 import workloads
+    q = workloads.fcc(1.0, 30.0)
+    box = (30.0, 30.0, 30.0)
+    a = gpu_build(cuda, q, 3.3, box, "full_csr", builds=1, use_graph=False)
+    b = gpu_build(cuda, q, 3.3, box, "full_csr", builds=4, use_graph=True)
+    assert np.array_equal(a["list"], b["list"]) and np.array_equal(a["off"], b["off"])
+    assert np.array_equal(a["sorted_ids"], b["sorted_ids"])
+
+
+def test_owned_subset_with_global_ids(cuda, oracle):
+    """Multi-GPU building block: rows only for the owned particles, partner ids mapped to global."""
+    from md_neighbor_list_b200 import VerletListB200, workloads
+    torch = cuda
+    L = 24.0
+    q = workloads.fcc(1.0, L)
+    n = q.shape[0]
+    rng = np.random.default_rng(4)
+    perm = rng.permutation(n).astype(np.int32)  # local index -> global id
+    n_owned = n // 3
+    ql = np.ascontiguousarray(q[perm])
+    for mode, builder in (("full_csr", oracle.build_full), ("half_csr", oracle.build_half)):
+        nl = VerletListB200(3.3, L, L, L, mode=mode)
+        nl.initialize(n)
+        nl.build(torch.from_numpy(ql).cuda(), n_owned=n_owned, global_ids=torch.from_numpy(perm).cuda())
+        st = nl.synchronize()
+        ref = builder(q, 3.3, (L, L, L)).sorted_rows()
+        cnt = nl.number_of_partners().cpu().numpy()
+        off = nl.offsets().cpu().numpy()
+        lst = sort_rows(oracle, nl.partners().cpu().numpy(), off)
+        assert st.n == n_owned and len(cnt) == n_owned
+        for li in range(0, n_owned, 37):
+            g = perm[li]
+            assert np.array_equal(lst[off[li]:off[li + 1]], ref.partners[ref.offsets[g]:ref.offsets[g + 1]])
+        assert np.array_equal(cnt, ref.number_of_partners[perm[:n_owned]])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs[2]: 16M uniform, density 1.0, SL 3.3)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1 << 21, 1 << 24])
+def test_large_uniform_properties(cuda, n):
+    """Size-independent properties at sizes no CPU oracle finishes quickly: CSR consistency, FULL = HALF mirrored
+    (count_full[i] = count_half[i] + #times i is a partner in HALF), checksum of checksums, no self pairs."""
+    from md_neighbor_list_b200 import VerletListB200, workloads
+    torch = cuda
+    L = float(round(n ** (1.0 / 3.0)))  # density ~1.0 (2^24 -> 256)
+    q = workloads.uniform(n, L)
+    qd = torch.from_numpy(q).cuda()
+    res = {}
+    for mode in ("half_csr", "full_csr"):
+        nl = VerletListB200(3.3, L, L, L, mode=mode)
+        nl.initialize(n)
+        nl.build(qd)
+        st = nl.synchronize()
+        cnt, off, lst = nl.number_of_partners(), nl.offsets(), nl.partners()
+        assert int(off[-1]) == st.number_of_pairs == int(cnt.sum(dtype=torch.int64))
+        assert bool((off[1:] - off[:-1] == cnt).all())
+        assert int(lst.min()) >= 0 and int(lst.max()) < n
+        rows = torch.repeat_interleave(torch.arange(n, device=lst.device, dtype=torch.int32), cnt.long())
+        if mode == "half_csr":
+            assert bool((lst > rows).all())
+            res["half_cnt"] = cnt.clone()
+            res["half_in"] = torch.bincount(lst.long(), minlength=n)
+            res["half_pairs"] = st.number_of_pairs
+        else:
+            assert bool((lst != rows).all())
+            assert st.number_of_pairs == 2 * res["half_pairs"]
+            assert bool((cnt.long() == res["half_cnt"].long() + res["half_in"]).all())
+            # checksum of checksums: sum of all partner ids == sum_i i * count[i] (the relation is symmetric)
+            lhs = int(lst.sum(dtype=torch.int64))
+            rhs = int((torch.arange(n, device=lst.device, dtype=torch.int64) * cnt.long()).sum())
+            assert lhs == rhs
+            # expected density of partners: n * rho * 4/3 pi SL^3 minus the open-boundary deficit
+            per = st.number_of_pairs / n
+            assert 0.8 * 150.5 < per < 150.5 * 1.01
+        del rows
+        nl.close()
+        torch.cuda.empty_cache()
