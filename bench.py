@@ -259,6 +259,8 @@ def run_ours(args):
     h_off = torch.empty(n_owned + 1, dtype=torch.int64).pin_memory()
     h_lst = torch.empty(n_entries, dtype=torch.int32).pin_memory()
     q_dev2 = torch.empty_like(q_dev)
+    # borrowed views of the library's output buffers (stable until reserve/destroy)
+    v_cnt, v_off, v_lst = nl.number_of_partners(), nl.offsets(), nl.partners()
 
     def one_e2e():
         q_dev2.copy_(q_pinned, non_blocking=True)
@@ -266,9 +268,9 @@ def run_ours(args):
             nl.build(q_dev2, stream=stream)
         else:
             halo.build(nl, q_dev2, stream)
-        h_cnt.copy_(nl.number_of_partners(), non_blocking=True)
-        h_off.copy_(nl.offsets(), non_blocking=True)
-        h_lst.copy_(nl.partners()[:n_entries], non_blocking=True)
+        h_cnt.copy_(v_cnt, non_blocking=True)
+        h_off.copy_(v_off, non_blocking=True)
+        h_lst.copy_(v_lst, non_blocking=True)
 
     with torch.cuda.stream(stream):
         for _ in range(2):
