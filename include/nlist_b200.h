@@ -49,7 +49,9 @@ typedef enum {
   NLB200_ERR_CAPACITY = 3,    /* partner-list capacity too small; nlb200_required_entries() tells how much */
   NLB200_ERR_OUT_OF_BOX = 4,  /* a particle lies more than one cell outside [0,L] (or is NaN) */
   NLB200_ERR_ELL_ROWS = 5,    /* a row is longer than the ELL row capacity (reference: silent overflow) */
-  NLB200_ERR_STATE = 6        /* call order violated (e.g. build before initialize) */
+  NLB200_ERR_STATE = 6,       /* call order violated (e.g. build before initialize) */
+  NLB200_ERR_CELL_CAPACITY = 7 /* a cell holds more particles than the pair-mask words cover (reference: NMAX_IN_MESH
+                                  = 70 unchecked, neighlist_gpu.hpp:74,111); nlb200_reserve_cell_capacity() grows it */
 } nlb200_status;
 
 /* Position element type — the reference's `Dtype` toggle, make_list.cu:6-12. */
@@ -82,7 +84,10 @@ typedef enum {
   /* 1: record a CUDA event between the stages of every build on the build's stream (disables graph replay);
    * read the per-stage device times with nlb200_get_stage_times.  The reference's counterpart is
    * `make cuda_profile=yes` + nvprof (Makefile:21,29-31). */
-  NLB200_OPT_PROFILE = 7
+  NLB200_OPT_PROFILE = 7,
+  /* most particles one cell may hold — the reference's NMAX_IN_MESH (neighlist_gpu.hpp:74).  0 (default): estimated
+   * from the mean occupancy at initialize (mean + 6 sigma).  Exceeding it is detected (NLB200_ERR_CELL_CAPACITY). */
+  NLB200_OPT_MAX_IN_CELL = 8
 } nlb200_option;
 
 typedef struct {
@@ -117,6 +122,10 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
 
 /* Grow (never shrink) the partner-list capacity; invalidates borrowed pointers. */
 int nlb200_reserve(nlb200_handle h, int64_t max_entries);
+
+/* Grow (never shrink) the per-cell particle capacity (NLB200_OPT_MAX_IN_CELL) after NLB200_ERR_CELL_CAPACITY;
+ * nlb200_get_stats().max_in_cell tells how much the last build needed. */
+int nlb200_reserve_cell_capacity(nlb200_handle h, int64_t max_in_cell);
 
 /* Replaces the destructors (neighlist_gpu.hpp:256-258, neighlist_cpu.hpp:396-398). */
 int nlb200_destroy(nlb200_handle h);

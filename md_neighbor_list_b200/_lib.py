@@ -11,11 +11,12 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libnlist_b200.so")
 
-OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_OUT_OF_BOX, ERR_ELL_ROWS, ERR_STATE = range(7)
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_OUT_OF_BOX, ERR_ELL_ROWS, ERR_STATE, ERR_CELL_CAPACITY = range(8)
 F32, F64 = 0, 1
 HALF_CSR, FULL_CSR, FULL_ELL_TRANSPOSED = 0, 1, 2
 OPT_POSITION_STRIDE, OPT_SORT_ROWS, OPT_ELL_ROWS, OPT_EXACT_ONLY, OPT_USE_GRAPH, OPT_KERNEL_VARIANT = 1, 2, 3, 4, 5, 6
 OPT_PROFILE = 7
+OPT_MAX_IN_CELL = 8
 
 
 class Stats(C.Structure):
@@ -34,6 +35,7 @@ SYMBOLS = {
     "nlb200_set_option": (C.c_int, [_vp, _i32, _i64]),
     "nlb200_initialize": (C.c_int, [_vp, _i64, _i64]),
     "nlb200_reserve": (C.c_int, [_vp, _i64]),
+    "nlb200_reserve_cell_capacity": (C.c_int, [_vp, _i64]),
     "nlb200_destroy": (C.c_int, [_vp]),
     "nlb200_build": (C.c_int, [_vp, _vp, _i64, _vp]),
     "nlb200_build_subset": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),

@@ -44,7 +44,12 @@ struct nlb200_context {
   int2* cell_rank = nullptr;
   int32_t* perm = nullptr;
   int32_t* sorted_ids = nullptr;
+  int32_t* slot_cell = nullptr;
   float4* rec = nullptr;
+  uint32_t* mask = nullptr;  // [27][mask_wi][mask_ncap] pair-mask words
+  int32_t mask_wi = 0;       // words per (row, stencil cell): cells may hold up to 32*mask_wi particles
+  int64_t mask_ncap = 0;
+  int64_t max_in_cell_opt = 0;  // NLB200_OPT_MAX_IN_CELL (0 = estimate from the density)
   int32_t* counts = nullptr;
   int64_t* offsets = nullptr;
   int32_t* offsets32 = nullptr;
@@ -70,7 +75,7 @@ struct nlb200_context {
   int64_t g_n = -1, g_owned = -1;
 
   // per-stage CUDA events (NLB200_OPT_PROFILE): ev[k] is recorded before stage k, ev[n_stages] after the last one
-  static constexpr int MAX_STAGES = 12;
+  static constexpr int MAX_STAGES = 16;
   cudaEvent_t ev[MAX_STAGES + 1] = {};
   int stage_id[MAX_STAGES] = {};
   int n_stages = 0;
@@ -79,9 +84,10 @@ struct nlb200_context {
 };
 
 enum StageId { ST_ZERO = 0, ST_BIN, ST_SCAN_CELLS, ST_SCATTER, ST_CELLSORT, ST_COUNT, ST_SCAN_COUNTS, ST_FILL,
-               ST_SORT_ROWS, ST_ELL, ST_STATUS, ST_NUM };
+               ST_SORT_ROWS, ST_ELL, ST_STATUS, ST_PAIRMASK, ST_ROWCOUNT, ST_EMIT, ST_NUM };
 static const char* const kStageNames[ST_NUM] = {"zero", "bin", "scan_cells", "scatter", "cellsort", "search_count",
-                                                "scan_counts", "search_fill", "sort_rows", "ell", "status_copy"};
+                                                "scan_counts", "search_fill", "sort_rows", "ell", "status_copy",
+                                                "pairmask", "row_count", "emit"};
 
 namespace {
 
@@ -145,6 +151,8 @@ void free_buffers(nlb200_context* h) {
   F(h->cell_rank);
   F(h->perm);
   F(h->sorted_ids);
+  F(h->slot_cell);
+  F(h->mask);
   F(h->rec);
   F(h->counts);
   F(h->offsets);
@@ -199,8 +207,41 @@ cudaError_t set_attr_ts() {
   if ((e = set_attr_e<T, STRIDE, true, false>()) != cudaSuccess) return e;
   return set_attr_e<T, STRIDE, true, true>();
 }
+constexpr int MAX_EMIT_SMEM = 200 * 1024;
+
+template <bool HALF, bool GID, bool COUNT>
+cudaError_t launch_emit_t(const EmitArgs& a, cudaStream_t s) {
+  emit_kernel<HALF, GID, COUNT><<<(unsigned)((a.n_total + EM_THREADS - 1) / EM_THREADS), EM_THREADS,
+                                  (size_t)a.stage_cap * sizeof(int32_t), s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_emit(bool half, bool count, const EmitArgs& a, cudaStream_t s) {
+  const bool gid = a.global_ids != nullptr;
+  if (!half) {
+    if (count) {
+      rowcount_kernel<<<(unsigned)((a.n_total + 127) / 128), 128, 0, s>>>(a);
+      return cudaGetLastError();
+    }
+    return gid ? launch_emit_t<false, true, false>(a, s) : launch_emit_t<false, false, false>(a, s);
+  }
+  if (count) return gid ? launch_emit_t<true, true, true>(a, s) : launch_emit_t<true, false, true>(a, s);
+  return gid ? launch_emit_t<true, true, false>(a, s) : launch_emit_t<true, false, false>(a, s);
+}
+
+template <bool HALF, bool GID, bool COUNT>
+cudaError_t set_emit_attr() {
+  return cudaFuncSetAttribute(emit_kernel<HALF, GID, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              MAX_EMIT_SMEM);
+}
+
 cudaError_t set_search_attrs() {
   cudaError_t e;
+  if ((e = set_emit_attr<false, false, false>()) != cudaSuccess) return e;
+  if ((e = set_emit_attr<false, true, false>()) != cudaSuccess) return e;
+  if ((e = set_emit_attr<true, false, false>()) != cudaSuccess) return e;
+  if ((e = set_emit_attr<true, true, false>()) != cudaSuccess) return e;
+  if ((e = set_emit_attr<true, false, true>()) != cudaSuccess) return e;
+  if ((e = set_emit_attr<true, true, true>()) != cudaSuccess) return e;
   if ((e = set_attr_ts<double, 4>()) != cudaSuccess) return e;
   if ((e = set_attr_ts<double, 3>()) != cudaSuccess) return e;
   if ((e = set_attr_ts<float, 4>()) != cudaSuccess) return e;
@@ -269,50 +310,104 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     CK(h, cudaGetLastError());
     CK(h, stage(ST_CELLSORT));
     const int64_t threads = (int64_t)M * 32;
-    cellsort_kernel<T, STRIDE><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(q, gp, h->cell_start, h->perm,
-                                                                                 h->sorted_ids, h->rec);
+    cellsort_kernel<T, STRIDE><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(
+        q, gp, h->cell_start, h->perm, h->sorted_ids, h->rec, h->slot_cell);
     CK(h, cudaGetLastError());
   }
-  // search geometry from the mean occupancy (no host sync: the maximum is not known here)
-  const double avg = (double)n_total / (double)M;
-  int block = (int)(std::ceil(avg * 1.25 / 32.0) * 32.0);
-  if (block < 32) block = 32;
-  if (block > 128) block = 128;
-  int64_t jt = (int64_t)(27.0 * avg * 1.5);
-  jt = (jt + 255) / 256 * 256;
-  if (jt < 512) jt = 512;
-  if (jt > 8192) jt = 8192;
-  const size_t smem = (size_t)jt * (sizeof(float4) + sizeof(int32_t));
-
-  SearchArgs<T> a;
-  a.q = q;
-  a.gp = gp;
-  a.cell_start = h->cell_start;
-  a.rec = h->rec;
-  a.global_ids = gids;
-  a.n_owned = (int32_t)n_owned;
-  a.counts = h->counts;
-  a.offsets = h->offsets;
-  a.partners = h->partners;
-  a.capacity = h->cap_entries;
-  a.st = h->status_dev;
-  a.jt = (int32_t)jt;
   const bool half = h->mode == NLB200_HALF_CSR;
-  CK(h, stage(ST_COUNT));
-  if (n > 0) {
-    CK(h, (launch_search<T, STRIDE>(half, false, h->exact_only != 0, a, M, block, smem, s)));
-  }
-  CK(h, stage(ST_SCAN_COUNTS));
-  {
-    const int tiles = (int)((n_owned + SCAN_TILE - 1) / SCAN_TILE);
-    scan_kernel<int64_t><<<tiles > 0 ? tiles : 1, SCAN_THREADS, 0, s>>>(
-        h->counts, n_owned, h->offsets, h->offsets32, h->scan_state_counts, h->status_dev,
-        &h->status_dev->max_partners, (long long)h->cap_entries);
-    CK(h, cudaGetLastError());
-  }
-  CK(h, stage(ST_FILL));
-  if (n > 0) {
-    CK(h, (launch_search<T, STRIDE>(half, true, h->exact_only != 0, a, M, block, smem, s)));
+  const bool use_v1 = h->exact_only != 0 || h->variant == 1;
+  if (use_v1) {
+    // --- v1: one CTA per cell, thread per particle, test evaluated twice (count, fill).  Kept for the exact-only
+    //     validation mode and as an ablation. ---
+    const double avg = (double)n_total / (double)M;
+    int block = (int)(std::ceil(avg * 1.25 / 32.0) * 32.0);
+    if (block < 32) block = 32;
+    if (block > 128) block = 128;
+    int64_t jt = (int64_t)(27.0 * avg * 1.5);
+    jt = (jt + 255) / 256 * 256;
+    if (jt < 512) jt = 512;
+    if (jt > 8192) jt = 8192;
+    const size_t smem = (size_t)jt * (sizeof(float4) + sizeof(int32_t));
+    SearchArgs<T> a;
+    a.q = q;
+    a.gp = gp;
+    a.cell_start = h->cell_start;
+    a.rec = h->rec;
+    a.global_ids = gids;
+    a.n_owned = (int32_t)n_owned;
+    a.counts = h->counts;
+    a.offsets = h->offsets;
+    a.partners = h->partners;
+    a.capacity = h->cap_entries;
+    a.st = h->status_dev;
+    a.jt = (int32_t)jt;
+    CK(h, stage(ST_COUNT));
+    if (n > 0) CK(h, (launch_search<T, STRIDE>(half, false, h->exact_only != 0, a, M, block, smem, s)));
+    CK(h, stage(ST_SCAN_COUNTS));
+    {
+      const int tiles = (int)((n_owned + SCAN_TILE - 1) / SCAN_TILE);
+      scan_kernel<int64_t><<<tiles > 0 ? tiles : 1, SCAN_THREADS, 0, s>>>(
+          h->counts, n_owned, h->offsets, h->offsets32, h->scan_state_counts, h->status_dev,
+          &h->status_dev->max_partners, (long long)h->cap_entries);
+      CK(h, cudaGetLastError());
+    }
+    CK(h, stage(ST_FILL));
+    if (n > 0) CK(h, (launch_search<T, STRIDE>(half, true, h->exact_only != 0, a, M, block, smem, s)));
+  } else {
+    // --- default: pair masks (every test once) -> row counts -> offsets -> staged, coalesced emission ---
+    PairMaskArgs<T> pm;
+    pm.q = q;
+    pm.gp = gp;
+    pm.cell_start = h->cell_start;
+    pm.rec = h->rec;
+    pm.sorted_ids = h->sorted_ids;
+    pm.n_owned = (int32_t)n_owned;
+    pm.mask = h->mask;
+    pm.n_cap = h->mask_ncap;
+    pm.wi = h->mask_wi;
+    pm.band = gp.band;
+    pm.st = h->status_dev;
+    EmitArgs em;
+    em.cell_start = h->cell_start;
+    em.sorted_ids = h->sorted_ids;
+    em.slot_cell = h->slot_cell;
+    em.global_ids = gids;
+    for (int d = 0; d < 3; d++) em.mesh[d] = gp.mesh[d];
+    em.n_total = n;
+    em.n_owned = (int32_t)n_owned;
+    em.mask = h->mask;
+    em.n_cap = h->mask_ncap;
+    em.wi = h->mask_wi;
+    em.counts = h->counts;
+    em.offsets = h->offsets;
+    em.partners = h->partners;
+    em.capacity = h->cap_entries;
+    {
+      // staging area of one emit CTA: EM_THREADS full rows of the expected length (+25 %); longer CTAs write direct
+      const double vol = h->L[0] * h->L[1] * h->L[2];
+      const double per = (double)n_total / vol * 4.18879020478639 * h->sl * h->sl * h->sl;
+      double cap = EM_THREADS * per * 1.25 + 512.0;
+      if (cap < 2048.0) cap = 2048.0;
+      if (cap > (double)(MAX_EMIT_SMEM / 4 - 1024)) cap = (double)(MAX_EMIT_SMEM / 4 - 1024);
+      em.stage_cap = (int32_t)cap;
+    }
+    CK(h, stage(ST_PAIRMASK));
+    if (n > 0) {
+      pairmask_kernel<T, STRIDE><<<(unsigned)M, PM_THREADS, (size_t)h->mask_wi * 32 * sizeof(float4), s>>>(pm);
+      CK(h, cudaGetLastError());
+    }
+    CK(h, stage(ST_ROWCOUNT));
+    if (n > 0) CK(h, launch_emit(half, true, em, s));
+    CK(h, stage(ST_SCAN_COUNTS));
+    {
+      const int tiles = (int)((n_owned + SCAN_TILE - 1) / SCAN_TILE);
+      scan_kernel<int64_t><<<tiles > 0 ? tiles : 1, SCAN_THREADS, 0, s>>>(
+          h->counts, n_owned, h->offsets, h->offsets32, h->scan_state_counts, h->status_dev,
+          &h->status_dev->max_partners, (long long)h->cap_entries);
+      CK(h, cudaGetLastError());
+    }
+    CK(h, stage(ST_EMIT));
+    if (n > 0) CK(h, launch_emit(half, false, em, s));
   }
   if (h->sort_rows) CK(h, stage(ST_SORT_ROWS));
   if (h->sort_rows && n_owned > 0) {
@@ -353,6 +448,24 @@ int64_t estimate_entries(const nlb200_context* h, int64_t n) {
   return (int64_t)e;
 }
 
+int alloc_mask(nlb200_context* h, int64_t max_in_cell) {
+  if (h->mask) cudaFree(h->mask);
+  h->mask = nullptr;
+  int64_t wi = (max_in_cell + 31) / 32;
+  if (wi < 1) wi = 1;
+  h->mask_wi = (int32_t)wi;
+  h->mask_ncap = (int64_t)align_up((size_t)(h->max_n > 0 ? h->max_n : 1), 32);
+  CK(h, cudaMalloc(&h->mask, sizeof(uint32_t) * (size_t)(27 * wi * h->mask_ncap)));
+  return NLB200_OK;
+}
+
+int64_t estimate_max_in_cell(const nlb200_context* h, int64_t n) {
+  // mean occupancy + 6 sigma of a Poisson cell count + slack; lattices stay well below (13-63 at
+  // mean 35.3).  Clustered inputs report NLB200_ERR_CELL_CAPACITY and the caller (or nlb200_build_host) grows it.
+  const double avg = (double)n / (double)h->n_cells;
+  return (int64_t)(avg + 6.0 * std::sqrt(avg) + 8.0);
+}
+
 int alloc_partners(nlb200_context* h, int64_t entries) {
   if (h->partners) cudaFree(h->partners);
   h->partners = nullptr;
@@ -376,6 +489,7 @@ const char* nlb200_status_string(int status) {
     case NLB200_ERR_OUT_OF_BOX: return "particle outside the box";
     case NLB200_ERR_ELL_ROWS: return "row longer than the ELL row capacity";
     case NLB200_ERR_STATE: return "invalid call order";
+    case NLB200_ERR_CELL_CAPACITY: return "a cell holds more particles than the pair-mask words cover";
   }
   return "unknown";
 }
@@ -425,6 +539,10 @@ int nlb200_set_option(nlb200_handle h, int option, int64_t value) {
     case NLB200_OPT_USE_GRAPH: h->use_graph = value != 0; return NLB200_OK;
     case NLB200_OPT_KERNEL_VARIANT: h->variant = (int)value; return NLB200_OK;
     case NLB200_OPT_PROFILE: h->profile = value != 0; return NLB200_OK;
+    case NLB200_OPT_MAX_IN_CELL:
+      if (value < 0 || value > (1 << 20)) return fail(h, NLB200_ERR_INVALID, "max particles per cell out of range");
+      h->max_in_cell_opt = value;
+      return NLB200_OK;
   }
   return fail(h, NLB200_ERR_INVALID, "unknown option %d", option);
 }
@@ -464,6 +582,7 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
   CK(h, cudaMalloc(&h->cell_rank, sizeof(int2) * (size_t)n));
   CK(h, cudaMalloc(&h->perm, sizeof(int32_t) * (size_t)n));
   CK(h, cudaMalloc(&h->sorted_ids, sizeof(int32_t) * (size_t)n));
+  CK(h, cudaMalloc(&h->slot_cell, sizeof(int32_t) * (size_t)n));
   CK(h, cudaMalloc(&h->rec, sizeof(float4) * (size_t)n));
   CK(h, cudaMalloc(&h->counts, sizeof(int32_t) * (size_t)(n + 8)));
   CK(h, cudaMalloc(&h->offsets, sizeof(int64_t) * (size_t)(n + 1)));
@@ -472,6 +591,8 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
   CK(h, cudaMemset(h->offsets32, 0, sizeof(int32_t) * (size_t)(n + 1)));
   const int64_t entries = max_entries > 0 ? max_entries : estimate_entries(h, n);
   int rc = alloc_partners(h, entries);
+  if (rc) return rc;
+  rc = alloc_mask(h, h->max_in_cell_opt > 0 ? h->max_in_cell_opt : estimate_max_in_cell(h, n));
   if (rc) return rc;
   if (h->mode == NLB200_FULL_ELL_TRANSPOSED) {
     // neighlist_gpu.hpp:102,271-274: MAX_PARTNERS * N ints, filled with -1 once
@@ -499,6 +620,15 @@ int nlb200_reserve(nlb200_handle h, int64_t max_entries) {
   drop_graph(h);
   h->have_result = false;
   return alloc_partners(h, max_entries);
+}
+
+int nlb200_reserve_cell_capacity(nlb200_handle h, int64_t max_in_cell) {
+  if (!h || !h->initialized) return h ? fail(h, NLB200_ERR_STATE, "reserve before initialize") : NLB200_ERR_INVALID;
+  if (max_in_cell <= (int64_t)h->mask_wi * 32) return NLB200_OK;
+  if (h->build_pending) CK(h, cudaStreamSynchronize(h->last_stream));
+  drop_graph(h);
+  h->have_result = false;
+  return alloc_mask(h, max_in_cell);
 }
 
 int nlb200_destroy(nlb200_handle h) {
@@ -599,6 +729,9 @@ int nlb200_synchronize(nlb200_handle h) {
   h->have_result = true;
   if (st.flags & FLAG_OUT_OF_BOX)
     return fail(h, NLB200_ERR_OUT_OF_BOX, "a particle lies more than one cell outside [0,L] or is NaN");
+  if (st.flags & FLAG_CELL_WORDS)
+    return fail(h, NLB200_ERR_CELL_CAPACITY, "a cell holds %d particles, the pair-mask words cover %d", st.max_in_cell,
+                h->mask_wi * 32);
   if (st.flags & FLAG_CAPACITY)
     return fail(h, NLB200_ERR_CAPACITY, "partner list needs %lld entries, capacity is %lld",
                 (long long)st.total_entries, (long long)h->cap_entries);
@@ -622,6 +755,13 @@ int nlb200_build_host(nlb200_handle h, const void* q_host, int64_t n, int32_t* n
   int rc = nlb200_build(h, h->q_stage, n, s);
   if (rc) return rc;
   rc = nlb200_synchronize(h);
+  if (rc == NLB200_ERR_CELL_CAPACITY) {
+    rc = nlb200_reserve_cell_capacity(h, h->stats.max_in_cell);
+    if (rc) return rc;
+    rc = nlb200_build(h, h->q_stage, n, s);
+    if (rc) return rc;
+    rc = nlb200_synchronize(h);
+  }
   if (rc == NLB200_ERR_CAPACITY) {
     // grow and retry once: the reference's answer to a full buffer is undefined behaviour
     const int64_t need = h->stats.required_entries;

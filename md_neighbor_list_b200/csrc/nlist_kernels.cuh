@@ -297,13 +297,15 @@ __global__ void __launch_bounds__(256) scatter_kernel(const int2* __restrict__ c
 // ---------------------------------------------------------------------------------------------------------------
 // 4. per-cell id sort (stable counting-sort order = ids ascending, neighlist_cpu.hpp:154-160) + physical reorder:
 //    rec[slot] = { float(x - cx*ms), float(y - cy*ms), float(z - cz*ms), id }   (cell-corner-relative FP32)
+//    sorted_ids[slot] = id, slot_cell[slot] = cell
 //    One warp per cell; rank sort with warp shuffles (O(n^2/32) per cell, n ~ 35).
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int STRIDE>
 __global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, GridParams<T> gp,
                                                        const int32_t* __restrict__ cell_start,
                                                        const int32_t* __restrict__ perm,
-                                                       int32_t* __restrict__ sorted_ids, float4* __restrict__ rec) {
+                                                       int32_t* __restrict__ sorted_ids, float4* __restrict__ rec,
+                                                       int32_t* __restrict__ slot_cell) {
   const int32_t cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (cell >= gp.n_cells) return;
   const int lane = lane_id();
@@ -334,6 +336,7 @@ __global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, 
       r.w = __int_as_float(id);
       sorted_ids[beg + rank] = id;
       rec[beg + rank] = r;
+      slot_cell[beg + rank] = cell;
     }
   }
 }
@@ -500,6 +503,385 @@ __global__ void __launch_bounds__(128) search_kernel(SearchArgs<T> a) {
   if (!FILL) {
     if (threadIdx.x == 0) atomicAdd(&a.st->candidates, (unsigned long long)ni * (unsigned long long)nj);
     if (band_local) atomicAdd(&a.st->band_tests, band_local);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 5-7 (default path).  "pair masks": every distance test is evaluated ONCE per ordered pair, its verdict kept as one
+// bit, and the CSR rows are expanded from the bits after the offsets are known.
+//
+//   pairmask_kernel   CTA = cell A.  The particles i of A sit in shared memory ({x, y, z, (|x|^2 - SL^2)/2} in the
+//                     frame centred on A).  The candidates j — the <= 9 contiguous x-runs of A's stencil in the
+//                     cell-sorted array — are spread over the LANES, PM_RJ per lane in registers, translated once into
+//                     A's frame ({x, y, z, -|x|^2/2}).  Lane utilisation follows the ~950-long candidate list (>= 93 %)
+//                     instead of the ~35 particles of a cell (55 % of two warps), and one broadcast LDS.128 feeds
+//                     PM_RJ tests (the shared-memory return path bounded the thread-per-i form,
+//                     profiles/r01_microbench_issue_rates.txt).
+//                     Test, dot form:  d = xi.xj - |xj|^2/2 - (|xi|^2 - SL^2)/2 = (SL^2 - r^2)/2   (3 FFMA + 1 FADD);
+//                     its sign bit is funnel-shifted into the lane's 32-bit word (1 SHF), min|d| is tracked (FMNMX).
+//                     After 32 particles of A the lane holds, for ITS candidate j, the word "which i of A are within
+//                     SL of j" — by symmetry a piece of ROW j.  Only a word whose min|d| fell inside the uncertainty
+//                     band E is revisited with the exact input-precision test.
+//                     mask[o][w][slot_j]: o = ordinal of A inside the stencil of j's cell, w = word (32 i's each).
+//   rowcount_kernel   thread = row: popcount (FULL) or id-filtered expansion (HALF) of the row's <= 27*WI words.
+//   scan_kernel       counts -> offsets (as before).
+//   emit_kernel       thread = row: expands set bits MSB-first (FLO) into a shared-memory staging area laid out as the
+//                     CTA's rows back to back; then warps copy each row to partners[offsets[id] ...] with coalesced
+//                     128-byte stores (scattered 4-byte stores cost more L2 sector writes than the whole test phase,
+//                     and at 16 M particles they turned into DRAM read-modify-writes).
+//   Rows come out in stencil order: cells ascending, ids ascending inside a cell — the discovery order of the
+//   reference kernels (kernel_impl.cuh:17-33).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PM_RJ = 4;         // candidates per lane
+constexpr int PM_THREADS = 128;  // 4 warps per cell
+constexpr uint32_t FLAG_CELL_WORDS = 16u;  // a cell holds more than 32*WI particles: mask words too narrow
+
+__device__ __forceinline__ int axis_lo(int c, int m) { return m == 3 ? 0 : max(c - 1, 0); }
+
+// (SL^2 - r^2)/2 in FP32, fixed evaluation order (recomputed bit-identically by the band re-test)
+__device__ __forceinline__ float pre_d(const float4& p, float xj, float yj, float zj, float wj) {
+  return __fsub_rn(__fmaf_rn(p.x, xj, __fmaf_rn(p.y, yj, __fmaf_rn(p.z, zj, wj))), p.w);
+}
+
+template <typename T>
+struct PairMaskArgs {
+  const T* q;  // caller's positions (band re-test only)
+  GridParams<T> gp;
+  const int32_t* cell_start;
+  const float4* rec;
+  const int32_t* sorted_ids;
+  int32_t n_owned;
+  uint32_t* mask;  // [27][wi][n_cap]
+  long long n_cap;
+  int32_t wi;
+  float band;
+  DeviceStatus* st;
+};
+
+template <typename T, int STRIDE>
+__global__ void __launch_bounds__(PM_THREADS) pairmask_kernel(PairMaskArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* si = reinterpret_cast<float4*>(smem_raw);  // [32 * wi]
+  __shared__ int32_t r_start[9], r_b1[9], r_b2[9], r_pre[10], r_dy[9], r_dz[9], r_o[9];
+  __shared__ int32_t s_xlo;
+
+  const GridParams<T>& gp = a.gp;
+  const int32_t mx = gp.mesh[0], my = gp.mesh[1], mz = gp.mesh[2];
+  const int32_t cell = blockIdx.x;
+  const int32_t ibeg = __ldg(a.cell_start + cell);
+  int32_t ni = __ldg(a.cell_start + cell + 1) - ibeg;
+  if (ni == 0) return;
+  if (ni > 32 * a.wi) {
+    if (threadIdx.x == 0) atomicOr(&a.st->flags, FLAG_CELL_WORDS);  // the build fails; keep memory accesses in range
+    ni = 32 * a.wi;
+  }
+  const int32_t cx = cell % mx;
+  const int32_t cy = (cell / mx) % my;
+  const int32_t cz = cell / (mx * my);
+
+  if (threadIdx.x == 0) {
+    int xlo, xhi, ylo, yhi, zlo, zhi;
+    axis_range(cx, mx, xlo, xhi);
+    axis_range(cy, my, ylo, yhi);
+    axis_range(cz, mz, zlo, zhi);
+    s_xlo = xlo;
+    int r = 0, pre = 0;
+    for (int z = zlo; z <= zhi; z++)
+      for (int y = ylo; y <= yhi; y++) {
+        const int32_t* cs = a.cell_start + (y + z * my) * mx;
+        const int32_t s0 = cs[xlo];
+        r_start[r] = s0;
+        r_b1[r] = (xlo + 1 <= xhi) ? cs[xlo + 1] : 0x7fffffff;
+        r_b2[r] = (xlo + 2 <= xhi) ? cs[xlo + 2] : 0x7fffffff;
+        r_dy[r] = y - cy;
+        r_dz[r] = z - cz;
+        // ordinal of A inside the stencil of the candidate's cell (x part added per candidate)
+        r_o[r] = ((cz - axis_lo(z, mz)) * 3 + (cy - axis_lo(y, my))) * 3;
+        r_pre[r] = pre;
+        pre += cs[xhi + 1] - s0;
+        r++;
+      }
+    for (; r < 9; r++) {
+      r_start[r] = 0;
+      r_b1[r] = r_b2[r] = 0x7fffffff;
+      r_dy[r] = r_dz[r] = r_o[r] = 0;
+      r_pre[r] = pre;
+    }
+    r_pre[9] = pre;
+  }
+  const float msx = gp.msf[0], msy = gp.msf[1], msz = gp.msf[2];
+  const float hx = 0.5f * msx, hy = 0.5f * msy, hz = 0.5f * msz;
+  for (int32_t k = threadIdx.x; k < ni; k += blockDim.x) {
+    const float4 r = __ldg(a.rec + ibeg + k);
+    const float x = r.x - hx, y = r.y - hy, z = r.z - hz;
+    si[k] = make_float4(x, y, z, 0.5f * (fmaf(x, x, fmaf(y, y, z * z)) - gp.sl2f));
+  }
+  __syncthreads();
+  const int32_t nj = r_pre[9];
+  const int32_t xlo = s_xlo;
+  const int lane = lane_id();
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int32_t nchunk = (nj + 32 * PM_RJ - 1) / (32 * PM_RJ);
+  unsigned long long band_local = 0;
+
+  for (int32_t chunk = warp; chunk < nchunk; chunk += nwarps) {
+    float xj[PM_RJ], yj[PM_RJ], zj[PM_RJ], wj[PM_RJ];
+    int32_t sj[PM_RJ];     // candidate's slot
+    int32_t oj[PM_RJ];     // mask plane (o * wi), -1: nothing to store (tail lane or ghost row)
+    int r = 0;
+#pragma unroll
+    for (int k = 0; k < PM_RJ; k++) {
+      const int32_t c = chunk * (32 * PM_RJ) + k * 32 + lane;
+      xj[k] = yj[k] = zj[k] = 0.f;
+      wj[k] = -1.0e30f;  // d = -1e30: a miss, far from the band
+      sj[k] = 0;
+      oj[k] = -1;
+      if (c < nj) {
+        while (c >= r_pre[r + 1]) r++;
+        const int32_t s = r_start[r] + (c - r_pre[r]);
+        const int32_t x = xlo + ((s >= r_b1[r]) ? 1 : 0) + ((s >= r_b2[r]) ? 1 : 0);
+        const float4 rj = __ldg(a.rec + s);
+        xj[k] = fmaf((float)(x - cx) - 0.5f, msx, rj.x);
+        yj[k] = fmaf((float)r_dy[r] - 0.5f, msy, rj.y);
+        zj[k] = fmaf((float)r_dz[r] - 0.5f, msz, rj.z);
+        wj[k] = -0.5f * fmaf(xj[k], xj[k], fmaf(yj[k], yj[k], zj[k] * zj[k]));
+        sj[k] = s;
+        if (__ldg(a.sorted_ids + s) < a.n_owned) oj[k] = (r_o[r] + (cx - axis_lo(x, mx))) * a.wi;
+      }
+    }
+    for (int32_t w = 0; w * 32 < ni; w++) {
+      const int32_t cnt = min(32, ni - w * 32);
+      const float4* sp = si + w * 32;
+      uint32_t miss[PM_RJ];
+#pragma unroll
+      for (int k = 0; k < PM_RJ; k++) miss[k] = 0u;
+      float m = 3.0e38f;
+#pragma unroll 4
+      for (int32_t ii = 0; ii < cnt; ii++) {
+        const float4 p = sp[ii];
+#pragma unroll
+        for (int k = 0; k < PM_RJ; k++) {
+          const float d = pre_d(p, xj[k], yj[k], zj[k], wj[k]);
+          miss[k] = __funnelshift_l(__float_as_uint(d), miss[k], 1);  // shift the sign bit in
+          m = fminf(m, fabsf(d));
+        }
+      }
+      uint32_t hits[PM_RJ];
+#pragma unroll
+      for (int k = 0; k < PM_RJ; k++) hits[k] = (~miss[k]) << (32 - cnt);  // bit (31 - ii) <-> particle w*32 + ii
+      if (m < a.band) {
+        // some test of this word fell inside the pre-filter's uncertainty band: decide those exactly (rare)
+#pragma unroll
+        for (int k = 0; k < PM_RJ; k++) {
+          if (oj[k] < 0) continue;
+          for (int32_t ii = 0; ii < cnt; ii++) {
+            const float d = pre_d(sp[ii], xj[k], yj[k], zj[k], wj[k]);
+            if (fabsf(d) < a.band) {
+              const int32_t iid = __ldg(a.sorted_ids + ibeg + w * 32 + ii);
+              const int32_t jid = __ldg(a.sorted_ids + sj[k]);
+              const bool hit = exact_within(load_pos<T, STRIDE>(a.q, iid), load_pos<T, STRIDE>(a.q, jid), gp.sl2);
+              const uint32_t bit = 0x80000000u >> ii;
+              hits[k] = hit ? (hits[k] | bit) : (hits[k] & ~bit);
+              band_local++;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < PM_RJ; k++)
+        if (oj[k] >= 0) a.mask[(long long)(oj[k] + w) * a.n_cap + sj[k]] = hits[k];
+    }
+  }
+  if (threadIdx.x == 0) atomicAdd(&a.st->candidates, (unsigned long long)ni * (unsigned long long)nj);
+  if (band_local) atomicAdd(&a.st->band_tests, band_local);
+}
+
+struct EmitArgs {
+  const int32_t* cell_start;
+  const int32_t* sorted_ids;
+  const int32_t* slot_cell;
+  const int32_t* global_ids;  // optional local -> global id map
+  int32_t mesh[3];
+  int32_t n_total, n_owned;
+  const uint32_t* mask;
+  long long n_cap;
+  int32_t wi;
+  int32_t* counts;
+  const int64_t* offsets;
+  int32_t* partners;
+  long long capacity;
+  int32_t stage_cap;  // entries of shared-memory staging per CTA
+};
+
+// Visits the mask words of the row held in `slot` (a particle of cell `cell`) in stencil order — cells ascending,
+// words ascending inside a cell — and calls f(word, first_slot): bit (31 - b) of `word` set <=> the particle in
+// cell-sorted slot first_slot + b is within SL.  The first two words of the three cells of an x-run (all of them
+// unless a cell holds more than 64 particles) are fetched by six independent loads before any is used.
+// CLEAR_SELF removes the row's own bit (FULL lists: j != i, kernel_impl.cuh:29).
+template <bool CLEAR_SELF, typename F>
+__device__ __forceinline__ void walk_words(const EmitArgs& a, int32_t slot, int32_t cell, F&& f) {
+  const int32_t mx = a.mesh[0], my = a.mesh[1], mz = a.mesh[2];
+  const int32_t bx = cell % mx, by = (cell / mx) % my, bz = cell / (mx * my);
+  int xlo, xhi, ylo, yhi, zlo, zhi;
+  axis_range(bx, mx, xlo, xhi);
+  axis_range(by, my, ylo, yhi);
+  axis_range(bz, mz, zlo, zhi);
+  const int32_t nx = xhi - xlo + 1;
+  const int32_t own = slot - __ldg(a.cell_start + cell);  // index inside the own cell
+  const uint32_t* mrow = a.mask + slot;
+  for (int z = zlo; z <= zhi; z++)
+    for (int y = ylo; y <= yhi; y++) {
+      const int32_t* cs = a.cell_start + (y + z * my) * mx + xlo;
+      int32_t cb[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) cb[k] = (k <= nx) ? __ldg(cs + k) : 0;
+      const int32_t o0 = ((z - zlo) * 3 + (y - ylo)) * 3 * a.wi;
+      int32_t nw[3];
+      uint32_t pre[3][2];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        nw[k] = (k < nx) ? min((cb[k + 1] - cb[k] + 31) >> 5, a.wi) : 0;  // > wi only after FLAG_CELL_WORDS
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+          pre[k][u] = (u < nw[k]) ? __ldg(mrow + (long long)(o0 + k * a.wi + u) * a.n_cap) : 0u;
+      }
+      const bool own_row = CLEAR_SELF && (z == bz) && (y == by);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const bool own_cell = own_row && (xlo + k == bx);
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          uint32_t word = pre[k][u];
+          if (own_cell && (own >> 5) == u) word &= ~(0x80000000u >> (own & 31));
+          if (word) f(word, cb[k] + 32 * u);
+        }
+        for (int32_t w = 2; w < nw[k]; w++) {
+          uint32_t word = __ldg(mrow + (long long)(o0 + k * a.wi + w) * a.n_cap);
+          if (own_cell && (own >> 5) == w) word &= ~(0x80000000u >> (own & 31));
+          if (word) f(word, cb[k] + 32 * w);
+        }
+      }
+    }
+}
+
+// FULL lists: the row length is a popcount.
+__global__ void __launch_bounds__(128) rowcount_kernel(EmitArgs a) {
+  const int32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= a.n_total) return;
+  const int32_t id = __ldg(a.sorted_ids + slot);
+  if (id >= a.n_owned) return;
+  int32_t cnt = 0;
+  walk_words<true>(a, slot, __ldg(a.slot_cell + slot), [&](uint32_t word, int32_t) { cnt += __popc(word); });
+  a.counts[id] = cnt;
+}
+
+constexpr int EM_THREADS = 64;
+
+// HALF:  rows keep the partners with a larger (global) id (neighlist_cpu.hpp:225-236).
+// COUNT: write counts[id] instead of partners (HALF lists need the ids to count).
+template <bool HALF, bool GID, bool COUNT>
+__global__ void __launch_bounds__(EM_THREADS) emit_kernel(EmitArgs a) {
+  extern __shared__ __align__(16) int32_t stage[];
+  __shared__ int32_t s_loc[EM_THREADS], s_len[EM_THREADS], s_id[EM_THREADS], s_wsum[EM_THREADS / 32];
+  __shared__ long long s_dst[EM_THREADS];
+  if (!COUNT) {
+    if (a.offsets[a.n_owned] > a.capacity) return;  // overflow already flagged by the offsets scan
+  }
+  const int32_t slot = blockIdx.x * EM_THREADS + threadIdx.x;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  int32_t id = 0x7fffffff;
+  if (slot < a.n_total) id = __ldg(a.sorted_ids + slot);
+  const bool owned = id < a.n_owned;
+  const int32_t cell = owned ? __ldg(a.slot_cell + slot) : 0;
+  // staged length of the row: every partner within SL (HALF rows are filtered by id while they are copied out)
+  int32_t len = 0;
+  if (owned) walk_words<!HALF>(a, slot, cell, [&](uint32_t word, int32_t) { len += __popc(word); });
+  // CTA-wide exclusive scan of the row lengths -> position of each row in the staging area
+  int32_t incl = len;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  int32_t wpre = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < EM_THREADS / 32; k++) {
+    const int32_t v = s_wsum[k];
+    if (k < warp) wpre += v;
+    total += v;
+  }
+  const int32_t loc = wpre + incl - len;
+  const int32_t mycmp = (GID && owned) ? __ldg(a.global_ids + id) : id;
+  const long long dst = (!COUNT && owned) ? (long long)a.offsets[id] : 0;
+  if (total > a.stage_cap) {
+    // rows too long for the staging area (dense clusters): every thread walks its row alone, uncoalesced
+    if (owned) {
+      int32_t* wp = a.partners + dst;
+      int32_t cnt = 0;
+      walk_words<!HALF>(a, slot, cell, [&](uint32_t word, int32_t first) {
+        while (word) {
+          const int b = __clz(word);
+          word &= ~(0x80000000u >> b);
+          int32_t pid = __ldg(a.sorted_ids + first + b);
+          if (GID) pid = __ldg(a.global_ids + pid);
+          if (HALF && !(pid > mycmp)) continue;
+          if (!COUNT) wp[cnt] = pid;
+          cnt++;
+        }
+      });
+      if (COUNT) a.counts[id] = cnt;
+    }
+    return;
+  }
+  s_loc[threadIdx.x] = loc;
+  s_len[threadIdx.x] = len;
+  s_id[threadIdx.x] = COUNT ? id : mycmp;
+  s_dst[threadIdx.x] = dst;
+  if (len > 0) {
+    // expansion: set bits -> cell-sorted slots of the partners; pure ALU + STS, no loads in the loop
+    int32_t* wp = stage + loc;
+    walk_words<!HALF>(a, slot, cell, [&](uint32_t word, int32_t first) {
+      do {
+        const int b = __clz(word);
+        word &= ~(0x80000000u >> b);
+        *wp++ = first + b;
+      } while (word);
+    });
+  }
+  __syncthreads();
+  // copy-out: one warp per row, partner ids gathered 32 at a time, coalesced stores
+  for (int r = warp; r < EM_THREADS; r += EM_THREADS / 32) {
+    const int32_t n = s_len[r];
+    if (n == 0 && !(HALF && COUNT)) continue;
+    const int32_t* src = stage + s_loc[r];
+    if (!HALF) {
+      int32_t* out = a.partners + s_dst[r];
+      for (int32_t t = lane; t < n; t += 32) {
+        int32_t pid = __ldg(a.sorted_ids + src[t]);
+        if (GID) pid = __ldg(a.global_ids + pid);
+        out[t] = pid;
+      }
+    } else {
+      int32_t rcmp = s_id[r];
+      if (COUNT && GID && rcmp < a.n_owned) rcmp = __ldg(a.global_ids + rcmp);
+      int32_t* out = a.partners + s_dst[r];
+      int32_t run = 0;
+      for (int32_t t0 = 0; t0 < n; t0 += 32) {
+        const int32_t t = t0 + lane;
+        int32_t pid = -2147483647 - 1;
+        if (t < n) {
+          pid = __ldg(a.sorted_ids + src[t]);
+          if (GID) pid = __ldg(a.global_ids + pid);
+        }
+        const bool keep = (t < n) && (pid > rcmp);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (!COUNT && keep) out[run + __popc(bal & ((1u << lane) - 1u))] = pid;
+        run += __popc(bal);
+      }
+      if (COUNT && lane == 0 && s_id[r] < a.n_owned) a.counts[s_id[r]] = run;
+    }
   }
 }
 

@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import (F32, F64, FULL_CSR, FULL_ELL_TRANSPOSED, HALF_CSR, OPT_ELL_ROWS, OPT_EXACT_ONLY,
-                   OPT_KERNEL_VARIANT, OPT_POSITION_STRIDE, OPT_PROFILE, OPT_SORT_ROWS, OPT_USE_GRAPH, NlistError,
+                   OPT_KERNEL_VARIANT, OPT_MAX_IN_CELL, OPT_POSITION_STRIDE, OPT_PROFILE, OPT_SORT_ROWS, OPT_USE_GRAPH, NlistError,
                    Stats, check)
 
 _MODES = {"half_csr": HALF_CSR, "full_csr": FULL_CSR, "full_ell_transposed": FULL_ELL_TRANSPOSED}
@@ -43,7 +43,7 @@ class VerletListB200:
 
     def __init__(self, search_length: float, Lx: float, Ly: float, Lz: float, dtype="f64", mode="full_csr",
                  position_stride: int = 4, sort_rows: bool = False, ell_rows: int = 200, exact_only: bool = False,
-                 use_graph: bool = True, kernel_variant: int = 0, profile: bool = False):
+                 use_graph: bool = True, kernel_variant: int = 0, profile: bool = False, max_in_cell: int = 0):
         self._lib = _lib.lib()
         self._h = C.c_void_p()
         self.dtype = _DTYPES[dtype]
@@ -56,7 +56,7 @@ class VerletListB200:
         for opt, val in ((OPT_POSITION_STRIDE, self.stride), (OPT_SORT_ROWS, int(sort_rows)),
                          (OPT_ELL_ROWS, self.ell_rows), (OPT_EXACT_ONLY, int(exact_only)),
                          (OPT_USE_GRAPH, int(use_graph)), (OPT_KERNEL_VARIANT, int(kernel_variant)),
-                         (OPT_PROFILE, int(profile))):
+                         (OPT_PROFILE, int(profile)), (OPT_MAX_IN_CELL, int(max_in_cell))):
             check(self._h, self._lib.nlb200_set_option(self._h, opt, val))
         self.n = 0
         self.device = None
@@ -69,6 +69,9 @@ class VerletListB200:
 
     def reserve(self, max_entries: int) -> None:
         check(self._h, self._lib.nlb200_reserve(self._h, int(max_entries)))
+
+    def reserve_cell_capacity(self, max_in_cell: int) -> None:
+        check(self._h, self._lib.nlb200_reserve_cell_capacity(self._h, int(max_in_cell)))
 
     def close(self) -> None:
         if self._h:

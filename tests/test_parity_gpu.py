@@ -25,15 +25,22 @@ def gpu_build(torch, q, sl, box, mode, dtype="f64", builds=1, max_entries=0, **o
         for _ in range(builds):
             nl.build(qd)
     from md_neighbor_list_b200 import NlistError, _lib
-    try:
-        st = nl.synchronize()
-    except NlistError as e:
-        if e.status != _lib.ERR_CAPACITY:
-            raise
-        nl.reserve(nl.stats().required_entries)
-        with torch.cuda.stream(stream):
-            nl.build(qd)
-        st = nl.synchronize()
+    for _ in range(4):
+        try:
+            st = nl.synchronize()
+            break
+        except NlistError as e:
+            # the two capacities the reference leaves unchecked are detected and can be grown (nlist_b200.h)
+            if e.status == _lib.ERR_CAPACITY:
+                nl.reserve(nl.stats().required_entries)
+            elif e.status == _lib.ERR_CELL_CAPACITY:
+                nl.reserve_cell_capacity(nl.stats().max_in_cell)
+            else:
+                raise
+            with torch.cuda.stream(stream):
+                nl.build(qd)
+    else:
+        raise AssertionError("capacity retries exhausted")
     out = {
         "np": nl.number_of_partners().cpu().numpy().copy(),
         "off": nl.offsets().cpu().numpy().copy(),
