@@ -40,6 +40,8 @@ struct nlb200_context {
   unsigned long long* scan_state_cells = nullptr;
   unsigned long long* scan_state_counts = nullptr;
   DeviceStatus* status_dev = nullptr;
+  int32_t* queue = nullptr;  // work counter of the persistent pair-mask kernel (inside zero_region)
+  int sm_count = 148;
   int32_t* cell_start = nullptr;
   int2* cell_rank = nullptr;
   int32_t* perm = nullptr;
@@ -211,17 +213,15 @@ constexpr int MAX_EMIT_SMEM = 200 * 1024;
 
 template <bool HALF, bool GID, bool COUNT>
 cudaError_t launch_emit_t(const EmitArgs& a, cudaStream_t s) {
-  emit_kernel<HALF, GID, COUNT><<<(unsigned)((a.n_total + EM_THREADS - 1) / EM_THREADS), EM_THREADS,
-                                  (size_t)a.stage_cap * sizeof(int32_t), s>>>(a);
+  constexpr int rows = EM_WARPS * 32;
+  emit_kernel<HALF, GID, COUNT><<<(unsigned)((a.n_total + rows - 1) / rows), rows,
+                                  (size_t)EM_WARPS * 32 * EM_LINE * sizeof(int32_t), s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_emit(bool half, bool count, const EmitArgs& a, cudaStream_t s) {
   const bool gid = a.global_ids != nullptr;
   if (!half) {
-    if (count) {
-      rowcount_kernel<<<(unsigned)((a.n_total + 127) / 128), 128, 0, s>>>(a);
-      return cudaGetLastError();
-    }
+    if (count) return cudaSuccess;  // FULL: the popcount pass already wrote counts[]
     return gid ? launch_emit_t<false, true, false>(a, s) : launch_emit_t<false, false, false>(a, s);
   }
   if (count) return gid ? launch_emit_t<true, true, true>(a, s) : launch_emit_t<true, false, true>(a, s);
@@ -234,8 +234,17 @@ cudaError_t set_emit_attr() {
                               MAX_EMIT_SMEM);
 }
 
+template <typename T, int STRIDE>
+cudaError_t set_pm_attr() {
+  return cudaFuncSetAttribute(pairmask_kernel<T, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM);
+}
+
 cudaError_t set_search_attrs() {
   cudaError_t e;
+  if ((e = set_pm_attr<double, 4>()) != cudaSuccess) return e;
+  if ((e = set_pm_attr<double, 3>()) != cudaSuccess) return e;
+  if ((e = set_pm_attr<float, 4>()) != cudaSuccess) return e;
+  if ((e = set_pm_attr<float, 3>()) != cudaSuccess) return e;
   if ((e = set_emit_attr<false, false, false>()) != cudaSuccess) return e;
   if ((e = set_emit_attr<false, true, false>()) != cudaSuccess) return e;
   if ((e = set_emit_attr<true, false, false>()) != cudaSuccess) return e;
@@ -362,6 +371,8 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     pm.rec = h->rec;
     pm.sorted_ids = h->sorted_ids;
     pm.n_owned = (int32_t)n_owned;
+    pm.has_ghosts = n_owned < n_total ? 1 : 0;
+    pm.queue = h->queue;
     pm.mask = h->mask;
     pm.n_cap = h->mask_ncap;
     pm.wi = h->mask_wi;
@@ -382,22 +393,35 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     em.offsets = h->offsets;
     em.partners = h->partners;
     em.capacity = h->cap_entries;
-    {
-      // staging area of one emit CTA: EM_THREADS full rows of the expected length (+25 %); longer CTAs write direct
-      const double vol = h->L[0] * h->L[1] * h->L[2];
-      const double per = (double)n_total / vol * 4.18879020478639 * h->sl * h->sl * h->sl;
-      double cap = EM_THREADS * per * 1.25 + 512.0;
-      if (cap < 2048.0) cap = 2048.0;
-      if (cap > (double)(MAX_EMIT_SMEM / 4 - 1024)) cap = (double)(MAX_EMIT_SMEM / 4 - 1024);
-      em.stage_cap = (int32_t)cap;
-    }
     CK(h, stage(ST_PAIRMASK));
     if (n > 0) {
-      pairmask_kernel<T, STRIDE><<<(unsigned)M, PM_THREADS, (size_t)h->mask_wi * 32 * sizeof(float4), s>>>(pm);
+      // persistent warps: as many CTAs as are resident at once, each warp draws cells from the queue
+      const size_t pm_smem = pm_warp_bytes(h->mask_wi) * (PM_THREADS / 32);
+      int per_sm = 0;
+      CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairmask_kernel<T, STRIDE>, PM_THREADS, pm_smem));
+      if (per_sm < 1) per_sm = 1;
+      int64_t grid = (int64_t)per_sm * h->sm_count;
+      // items per cell: at least ~4 items per resident warp so that the queue can balance a small system
+      const int64_t resident = grid * (PM_THREADS / 32);
+      int64_t parts = (4 * resident + M - 1) / M;
+      if (parts < 1) parts = 1;
+      if (parts > 8) parts = 8;
+      if (h->variant >= 100 && h->variant < 200) parts = h->variant - 100;  // tuning override
+      pm.parts = (int32_t)parts;
+      const int64_t need = (M * parts + PM_THREADS / 32 - 1) / (PM_THREADS / 32);
+      if (grid > need) grid = need;
+      pairmask_kernel<T, STRIDE><<<(unsigned)grid, PM_THREADS, pm_smem, s>>>(pm);
       CK(h, cudaGetLastError());
     }
     CK(h, stage(ST_ROWCOUNT));
-    if (n > 0) CK(h, launch_emit(half, true, em, s));
+    if (n > 0) {
+      if (half) {
+        CK(h, launch_emit(true, true, em, s));
+      } else {
+        rowcount_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(em);
+        CK(h, cudaGetLastError());
+      }
+    }
     CK(h, stage(ST_SCAN_COUNTS));
     {
       const int tiles = (int)((n_owned + SCAN_TILE - 1) / SCAN_TILE);
@@ -572,12 +596,16 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
   off = align_up(off + sizeof(unsigned long long) * (size_t)(h->tiles_n + 1), 256);
   const size_t o_st = off;
   off = align_up(off + sizeof(DeviceStatus), 256);
+  const size_t o_q = off;
+  off = align_up(off + sizeof(int32_t), 256);
   h->zero_bytes = off;
   CK(h, cudaMalloc(&h->zero_region, off));
   h->cell_count = reinterpret_cast<int32_t*>(h->zero_region + o_count);
   h->scan_state_cells = reinterpret_cast<unsigned long long*>(h->zero_region + o_sc);
   h->scan_state_counts = reinterpret_cast<unsigned long long*>(h->zero_region + o_sn);
   h->status_dev = reinterpret_cast<DeviceStatus*>(h->zero_region + o_st);
+  h->queue = reinterpret_cast<int32_t*>(h->zero_region + o_q);
+  CK(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
   CK(h, cudaMalloc(&h->cell_start, sizeof(int32_t) * (size_t)(M + 1)));
   CK(h, cudaMalloc(&h->cell_rank, sizeof(int2) * (size_t)n));
   CK(h, cudaMalloc(&h->perm, sizeof(int32_t) * (size_t)n));

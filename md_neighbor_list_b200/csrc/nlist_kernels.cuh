@@ -551,148 +551,188 @@ struct PairMaskArgs {
   const float4* rec;
   const int32_t* sorted_ids;
   int32_t n_owned;
-  uint32_t* mask;  // [27][wi][n_cap]
+  int32_t has_ghosts;  // n_owned < n_total: rows of ghost particles are skipped
+  uint32_t* mask;      // [27][wi][n_cap]
   long long n_cap;
   int32_t wi;
   float band;
+  int32_t* queue;  // item counter (zeroed per build): warps draw (cell, part) items from it
+  int32_t parts;   // items per cell: part p takes the candidate chunks p, p + parts, ...  (small systems: more
+                   // items than resident warps, so that the queue can balance them)
   DeviceStatus* st;
 };
+
+// per-warp shared memory: the cell's particles + its run table
+constexpr int PM_TAB = 64;  // ints: start[9] b1[9] b2[9] pre[10] o[9] ty[9] tz[9]
+__host__ __device__ inline size_t pm_warp_bytes(int wi) { return (size_t)wi * 32 * sizeof(float4) + PM_TAB * 4; }
 
 template <typename T, int STRIDE>
 __global__ void __launch_bounds__(PM_THREADS) pairmask_kernel(PairMaskArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* si = reinterpret_cast<float4*>(smem_raw);  // [32 * wi]
-  __shared__ int32_t r_start[9], r_b1[9], r_b2[9], r_pre[10], r_dy[9], r_dz[9], r_o[9];
-  __shared__ int32_t s_xlo;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  unsigned char* wbase = smem_raw + (size_t)warp * pm_warp_bytes(a.wi);
+  float4* si = reinterpret_cast<float4*>(wbase);  // [32 * wi]
+  int32_t* t_start = reinterpret_cast<int32_t*>(wbase + (size_t)a.wi * 32 * sizeof(float4));
+  int32_t* t_b1 = t_start + 9;
+  int32_t* t_b2 = t_b1 + 9;
+  int32_t* t_pre = t_b2 + 9;  // [10]
+  int32_t* t_o = t_pre + 10;
+  float* t_ty = reinterpret_cast<float*>(t_o + 9);
+  float* t_tz = t_ty + 9;
 
   const GridParams<T>& gp = a.gp;
   const int32_t mx = gp.mesh[0], my = gp.mesh[1], mz = gp.mesh[2];
-  const int32_t cell = blockIdx.x;
-  const int32_t ibeg = __ldg(a.cell_start + cell);
-  int32_t ni = __ldg(a.cell_start + cell + 1) - ibeg;
-  if (ni == 0) return;
-  if (ni > 32 * a.wi) {
-    if (threadIdx.x == 0) atomicOr(&a.st->flags, FLAG_CELL_WORDS);  // the build fails; keep memory accesses in range
-    ni = 32 * a.wi;
-  }
-  const int32_t cx = cell % mx;
-  const int32_t cy = (cell / mx) % my;
-  const int32_t cz = cell / (mx * my);
-
-  if (threadIdx.x == 0) {
-    int xlo, xhi, ylo, yhi, zlo, zhi;
-    axis_range(cx, mx, xlo, xhi);
-    axis_range(cy, my, ylo, yhi);
-    axis_range(cz, mz, zlo, zhi);
-    s_xlo = xlo;
-    int r = 0, pre = 0;
-    for (int z = zlo; z <= zhi; z++)
-      for (int y = ylo; y <= yhi; y++) {
-        const int32_t* cs = a.cell_start + (y + z * my) * mx;
-        const int32_t s0 = cs[xlo];
-        r_start[r] = s0;
-        r_b1[r] = (xlo + 1 <= xhi) ? cs[xlo + 1] : 0x7fffffff;
-        r_b2[r] = (xlo + 2 <= xhi) ? cs[xlo + 2] : 0x7fffffff;
-        r_dy[r] = y - cy;
-        r_dz[r] = z - cz;
-        // ordinal of A inside the stencil of the candidate's cell (x part added per candidate)
-        r_o[r] = ((cz - axis_lo(z, mz)) * 3 + (cy - axis_lo(y, my))) * 3;
-        r_pre[r] = pre;
-        pre += cs[xhi + 1] - s0;
-        r++;
-      }
-    for (; r < 9; r++) {
-      r_start[r] = 0;
-      r_b1[r] = r_b2[r] = 0x7fffffff;
-      r_dy[r] = r_dz[r] = r_o[r] = 0;
-      r_pre[r] = pre;
-    }
-    r_pre[9] = pre;
-  }
   const float msx = gp.msf[0], msy = gp.msf[1], msz = gp.msf[2];
   const float hx = 0.5f * msx, hy = 0.5f * msy, hz = 0.5f * msz;
-  for (int32_t k = threadIdx.x; k < ni; k += blockDim.x) {
-    const float4 r = __ldg(a.rec + ibeg + k);
-    const float x = r.x - hx, y = r.y - hy, z = r.z - hz;
-    si[k] = make_float4(x, y, z, 0.5f * (fmaf(x, x, fmaf(y, y, z * z)) - gp.sl2f));
-  }
-  __syncthreads();
-  const int32_t nj = r_pre[9];
-  const int32_t xlo = s_xlo;
-  const int lane = lane_id();
-  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int32_t nchunk = (nj + 32 * PM_RJ - 1) / (32 * PM_RJ);
-  unsigned long long band_local = 0;
+  unsigned long long band_local = 0, cand_local = 0;
 
-  for (int32_t chunk = warp; chunk < nchunk; chunk += nwarps) {
-    float xj[PM_RJ], yj[PM_RJ], zj[PM_RJ], wj[PM_RJ];
-    int32_t sj[PM_RJ];     // candidate's slot
-    int32_t oj[PM_RJ];     // mask plane (o * wi), -1: nothing to store (tail lane or ghost row)
-    int r = 0;
-#pragma unroll
-    for (int k = 0; k < PM_RJ; k++) {
-      const int32_t c = chunk * (32 * PM_RJ) + k * 32 + lane;
-      xj[k] = yj[k] = zj[k] = 0.f;
-      wj[k] = -1.0e30f;  // d = -1e30: a miss, far from the band
-      sj[k] = 0;
-      oj[k] = -1;
-      if (c < nj) {
-        while (c >= r_pre[r + 1]) r++;
-        const int32_t s = r_start[r] + (c - r_pre[r]);
-        const int32_t x = xlo + ((s >= r_b1[r]) ? 1 : 0) + ((s >= r_b2[r]) ? 1 : 0);
-        const float4 rj = __ldg(a.rec + s);
-        xj[k] = fmaf((float)(x - cx) - 0.5f, msx, rj.x);
-        yj[k] = fmaf((float)r_dy[r] - 0.5f, msy, rj.y);
-        zj[k] = fmaf((float)r_dz[r] - 0.5f, msz, rj.z);
-        wj[k] = -0.5f * fmaf(xj[k], xj[k], fmaf(yj[k], yj[k], zj[k] * zj[k]));
-        sj[k] = s;
-        if (__ldg(a.sorted_ids + s) < a.n_owned) oj[k] = (r_o[r] + (cx - axis_lo(x, mx))) * a.wi;
+  const long long n_items = (long long)gp.n_cells * a.parts;
+  int32_t item = 0;
+  if (lane == 0) item = atomicAdd(a.queue, 1);
+  item = __shfl_sync(0xffffffffu, item, 0);
+  while (item < n_items) {
+    const int32_t cell = item / a.parts, part = item - cell * a.parts;
+    int32_t next = 0;
+    if (lane == 0) next = atomicAdd(a.queue, 1);  // in flight while this cell is processed
+    const int32_t ibeg = __ldg(a.cell_start + cell);
+    int32_t ni = __ldg(a.cell_start + cell + 1) - ibeg;
+    if (ni > 0) {
+      if (ni > 32 * a.wi) {
+        if (lane == 0 && part == 0) atomicOr(&a.st->flags, FLAG_CELL_WORDS);  // the build fails; stay in range
+        ni = 32 * a.wi;
       }
-    }
-    for (int32_t w = 0; w * 32 < ni; w++) {
-      const int32_t cnt = min(32, ni - w * 32);
-      const float4* sp = si + w * 32;
-      uint32_t miss[PM_RJ];
-#pragma unroll
-      for (int k = 0; k < PM_RJ; k++) miss[k] = 0u;
-      float m = 3.0e38f;
-#pragma unroll 4
-      for (int32_t ii = 0; ii < cnt; ii++) {
-        const float4 p = sp[ii];
-#pragma unroll
-        for (int k = 0; k < PM_RJ; k++) {
-          const float d = pre_d(p, xj[k], yj[k], zj[k], wj[k]);
-          miss[k] = __funnelshift_l(__float_as_uint(d), miss[k], 1);  // shift the sign bit in
-          m = fminf(m, fabsf(d));
+      const int32_t cx = cell % mx;
+      const int32_t cy = (cell / mx) % my;
+      const int32_t cz = cell / (mx * my);
+      int xlo, xhi, ylo, yhi, zlo, zhi;
+      axis_range(cx, mx, xlo, xhi);
+      axis_range(cy, my, ylo, yhi);
+      axis_range(cz, mz, zlo, zhi);
+      const int32_t ny = yhi - ylo + 1, nruns = ny * (zhi - zlo + 1);
+      __syncwarp();  // the previous cell's readers are done
+      {
+        // run table: lane r describes run r = (z, y); prefix of the run lengths by warp scan
+        int32_t len = 0, s0 = 0, b1 = 0x7fffffff, b2 = 0x7fffffff, o = 0;
+        float ty = 0.f, tz = 0.f;
+        if (lane < nruns) {
+          const int z = zlo + lane / ny, y = ylo + lane % ny;
+          const int32_t* cs = a.cell_start + (y + z * my) * mx;
+          s0 = __ldg(cs + xlo);
+          if (xlo + 1 <= xhi) b1 = __ldg(cs + xlo + 1);
+          if (xlo + 2 <= xhi) b2 = __ldg(cs + xlo + 2);
+          len = __ldg(cs + xhi + 1) - s0;
+          ty = (float)(y - cy) - 0.5f;
+          tz = (float)(z - cz) - 0.5f;
+          // ordinal of this cell inside the stencil of the candidate's cell (x part added per candidate)
+          o = ((cz - axis_lo(z, mz)) * 3 + (cy - axis_lo(y, my))) * 3;
         }
-      }
-      uint32_t hits[PM_RJ];
+        int32_t incl = len;
 #pragma unroll
-      for (int k = 0; k < PM_RJ; k++) hits[k] = (~miss[k]) << (32 - cnt);  // bit (31 - ii) <-> particle w*32 + ii
-      if (m < a.band) {
-        // some test of this word fell inside the pre-filter's uncertainty band: decide those exactly (rare)
+        for (int d = 1; d < 16; d <<= 1) {
+          const int32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += v;
+        }
+        if (lane < 9) {
+          t_start[lane] = s0;
+          t_b1[lane] = b1;
+          t_b2[lane] = b2;
+          t_o[lane] = o;
+          t_ty[lane] = ty;
+          t_tz[lane] = tz;
+        }
+        if (lane < 10) t_pre[lane] = incl - len;  // lane 9: len = 0 -> the total
+      }
+      for (int32_t k = lane; k < ni; k += 32) {
+        const float4 r = __ldg(a.rec + ibeg + k);
+        const float x = r.x - hx, y = r.y - hy, z = r.z - hz;
+        si[k] = make_float4(x, y, z, 0.5f * (fmaf(x, x, fmaf(y, y, z * z)) - gp.sl2f));
+      }
+      __syncwarp();
+      const int32_t nj = t_pre[9];
+      if (lane == 0 && part == 0) cand_local += (unsigned long long)ni * (unsigned long long)nj;
+      const float tx0 = (float)(xlo - cx) - 0.5f;
+
+      for (int32_t c0 = part * (32 * PM_RJ); c0 < nj; c0 += a.parts * (32 * PM_RJ)) {
+        float xj[PM_RJ], yj[PM_RJ], zj[PM_RJ], wj[PM_RJ];
+        int32_t sj[PM_RJ];    // candidate's slot
+        uint32_t* mp[PM_RJ];  // its mask word for this cell (nullptr: tail lane or ghost row)
+        int r = 0;
 #pragma unroll
         for (int k = 0; k < PM_RJ; k++) {
-          if (oj[k] < 0) continue;
-          for (int32_t ii = 0; ii < cnt; ii++) {
-            const float d = pre_d(sp[ii], xj[k], yj[k], zj[k], wj[k]);
-            if (fabsf(d) < a.band) {
-              const int32_t iid = __ldg(a.sorted_ids + ibeg + w * 32 + ii);
-              const int32_t jid = __ldg(a.sorted_ids + sj[k]);
-              const bool hit = exact_within(load_pos<T, STRIDE>(a.q, iid), load_pos<T, STRIDE>(a.q, jid), gp.sl2);
-              const uint32_t bit = 0x80000000u >> ii;
-              hits[k] = hit ? (hits[k] | bit) : (hits[k] & ~bit);
-              band_local++;
+          const int32_t c = c0 + k * 32 + lane;
+          xj[k] = yj[k] = zj[k] = 0.f;
+          wj[k] = -1.0e30f;  // d = -1e30: a miss, far from the band
+          sj[k] = 0;
+          mp[k] = nullptr;
+          if (c < nj) {
+            while (c >= t_pre[r + 1]) r++;
+            const int32_t s = t_start[r] + (c - t_pre[r]);
+            const int32_t col = ((s >= t_b1[r]) ? 1 : 0) + ((s >= t_b2[r]) ? 1 : 0);
+            const float4 rj = __ldg(a.rec + s);
+            xj[k] = fmaf(tx0 + (float)col, msx, rj.x);
+            yj[k] = fmaf(t_ty[r], msy, rj.y);
+            zj[k] = fmaf(t_tz[r], msz, rj.z);
+            wj[k] = -0.5f * fmaf(xj[k], xj[k], fmaf(yj[k], yj[k], zj[k] * zj[k]));
+            sj[k] = s;
+            bool store = true;
+            if (a.has_ghosts) store = __ldg(a.sorted_ids + s) < a.n_owned;
+            if (store) {
+              const int32_t o = t_o[r] + (cx - axis_lo(xlo + col, mx));
+              mp[k] = a.mask + (long long)(o * a.wi) * a.n_cap + s;
             }
           }
         }
-      }
+        for (int32_t w = 0; w * 32 < ni; w++) {
+          const int32_t cnt = min(32, ni - w * 32);
+          const float4* sp = si + w * 32;
+          uint32_t miss[PM_RJ];
 #pragma unroll
-      for (int k = 0; k < PM_RJ; k++)
-        if (oj[k] >= 0) a.mask[(long long)(oj[k] + w) * a.n_cap + sj[k]] = hits[k];
+          for (int k = 0; k < PM_RJ; k++) miss[k] = 0u;
+          float m = 3.0e38f;
+#pragma unroll 4
+          for (int32_t ii = 0; ii < cnt; ii++) {
+            const float4 p = sp[ii];
+#pragma unroll
+            for (int k = 0; k < PM_RJ; k++) {
+              const float d = pre_d(p, xj[k], yj[k], zj[k], wj[k]);
+              miss[k] = __funnelshift_l(__float_as_uint(d), miss[k], 1);  // shift the sign bit in
+              m = fminf(m, fabsf(d));
+            }
+          }
+          uint32_t hits[PM_RJ];
+#pragma unroll
+          for (int k = 0; k < PM_RJ; k++) hits[k] = (~miss[k]) << (32 - cnt);  // bit (31 - ii) <-> particle w*32+ii
+          if (m < a.band) {
+            // some test of this word fell inside the pre-filter's uncertainty band: decide those exactly (rare)
+#pragma unroll
+            for (int k = 0; k < PM_RJ; k++) {
+              if (mp[k] == nullptr) continue;
+              for (int32_t ii = 0; ii < cnt; ii++) {
+                const float d = pre_d(sp[ii], xj[k], yj[k], zj[k], wj[k]);
+                if (fabsf(d) < a.band) {
+                  const int32_t iid = __ldg(a.sorted_ids + ibeg + w * 32 + ii);
+                  const int32_t jid = __ldg(a.sorted_ids + sj[k]);
+                  const bool hit =
+                      exact_within(load_pos<T, STRIDE>(a.q, iid), load_pos<T, STRIDE>(a.q, jid), gp.sl2);
+                  const uint32_t bit = 0x80000000u >> ii;
+                  hits[k] = hit ? (hits[k] | bit) : (hits[k] & ~bit);
+                  band_local++;
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < PM_RJ; k++)
+            if (mp[k] != nullptr) {
+              *mp[k] = hits[k];
+              mp[k] += a.n_cap;
+            }
+        }
+      }
     }
+    item = __shfl_sync(0xffffffffu, next, 0);
   }
-  if (threadIdx.x == 0) atomicAdd(&a.st->candidates, (unsigned long long)ni * (unsigned long long)nj);
+  if (cand_local) atomicAdd(&a.st->candidates, cand_local);
   if (band_local) atomicAdd(&a.st->band_tests, band_local);
 }
 
@@ -710,7 +750,6 @@ struct EmitArgs {
   const int64_t* offsets;
   int32_t* partners;
   long long capacity;
-  int32_t stage_cap;  // entries of shared-memory staging per CTA
 };
 
 // Visits the mask words of the row held in `slot` (a particle of cell `cell`) in stencil order — cells ascending,
@@ -764,7 +803,7 @@ __device__ __forceinline__ void walk_words(const EmitArgs& a, int32_t slot, int3
     }
 }
 
-// FULL lists: the row length is a popcount.
+// FULL lists: the row length is a popcount of the row's mask words (without its own bit).
 __global__ void __launch_bounds__(128) rowcount_kernel(EmitArgs a) {
   const int32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= a.n_total) return;
@@ -775,114 +814,214 @@ __global__ void __launch_bounds__(128) rowcount_kernel(EmitArgs a) {
   a.counts[id] = cnt;
 }
 
-constexpr int EM_THREADS = 64;
+// emit_kernel: thread = row, warp = 32 consecutive cell-sorted slots; warps are independent (no CTA barrier).
+//   Each lane expands the set bits of its row's words, MSB first (FLO), into its line of a [32][EM_TILE] shared-memory
+//   tile; the three cells of an x-run are expanded as three interleaved dependency chains whose write positions
+//   follow from popcounts.  When a line could overflow, the warp flushes the tile: row by row, the staged cell-sorted
+//   slots are turned into partner ids (gather from sorted_ids / global_ids) and stored with coalesced 128-byte
+//   stores at partners[offsets[id] + done ...].  4 KB of tile per warp instead of whole rows keeps ~24 warps per SM
+//   resident; the expansion is a chain of dependent ALU/XU ops and needs that many to hide its latency.
+// HALF:  rows keep the partners with a larger (global) id (neighlist_cpu.hpp:225-236); the filter runs in the flush
+//        (ballot compaction).  COUNT: write counts[id] instead of partners (HALF lists need the ids to count).
+constexpr int EM_WARPS = 4;
+constexpr int EM_TILE = 64;
+constexpr int EM_LINE = EM_TILE + 1;  // +1: lanes with equal fill hit different banks
 
-// HALF:  rows keep the partners with a larger (global) id (neighlist_cpu.hpp:225-236).
-// COUNT: write counts[id] instead of partners (HALF lists need the ids to count).
 template <bool HALF, bool GID, bool COUNT>
-__global__ void __launch_bounds__(EM_THREADS) emit_kernel(EmitArgs a) {
-  extern __shared__ __align__(16) int32_t stage[];
-  __shared__ int32_t s_loc[EM_THREADS], s_len[EM_THREADS], s_id[EM_THREADS], s_wsum[EM_THREADS / 32];
-  __shared__ long long s_dst[EM_THREADS];
+__global__ void __launch_bounds__(EM_WARPS * 32) emit_kernel(EmitArgs a) {
+  extern __shared__ __align__(16) int32_t em_smem[];
   if (!COUNT) {
     if (a.offsets[a.n_owned] > a.capacity) return;  // overflow already flagged by the offsets scan
   }
-  const int32_t slot = blockIdx.x * EM_THREADS + threadIdx.x;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
+  int32_t* tile = em_smem + warp * 32 * EM_LINE;
+  int32_t* line = tile + lane * EM_LINE;
+  const int32_t slot = (blockIdx.x * EM_WARPS + warp) * 32 + lane;
   int32_t id = 0x7fffffff;
   if (slot < a.n_total) id = __ldg(a.sorted_ids + slot);
   const bool owned = id < a.n_owned;
   const int32_t cell = owned ? __ldg(a.slot_cell + slot) : 0;
-  // staged length of the row: every partner within SL (HALF rows are filtered by id while they are copied out)
-  int32_t len = 0;
-  if (owned) walk_words<!HALF>(a, slot, cell, [&](uint32_t word, int32_t) { len += __popc(word); });
-  // CTA-wide exclusive scan of the row lengths -> position of each row in the staging area
-  int32_t incl = len;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += o;
-  }
-  if (lane == 31) s_wsum[warp] = incl;
-  __syncthreads();
-  int32_t wpre = 0, total = 0;
-#pragma unroll
-  for (int k = 0; k < EM_THREADS / 32; k++) {
-    const int32_t v = s_wsum[k];
-    if (k < warp) wpre += v;
-    total += v;
-  }
-  const int32_t loc = wpre + incl - len;
-  const int32_t mycmp = (GID && owned) ? __ldg(a.global_ids + id) : id;
+  const int32_t rcmp = (HALF && owned) ? (GID ? __ldg(a.global_ids + id) : id) : 0;
   const long long dst = (!COUNT && owned) ? (long long)a.offsets[id] : 0;
-  if (total > a.stage_cap) {
-    // rows too long for the staging area (dense clusters): every thread walks its row alone, uncoalesced
-    if (owned) {
-      int32_t* wp = a.partners + dst;
-      int32_t cnt = 0;
-      walk_words<!HALF>(a, slot, cell, [&](uint32_t word, int32_t first) {
-        while (word) {
-          const int b = __clz(word);
-          word &= ~(0x80000000u >> b);
-          int32_t pid = __ldg(a.sorted_ids + first + b);
-          if (GID) pid = __ldg(a.global_ids + pid);
-          if (HALF && !(pid > mycmp)) continue;
-          if (!COUNT) wp[cnt] = pid;
-          cnt++;
-        }
-      });
-      if (COUNT) a.counts[id] = cnt;
-    }
-    return;
-  }
-  s_loc[threadIdx.x] = loc;
-  s_len[threadIdx.x] = len;
-  s_id[threadIdx.x] = COUNT ? id : mycmp;
-  s_dst[threadIdx.x] = dst;
-  if (len > 0) {
-    // expansion: set bits -> cell-sorted slots of the partners; pure ALU + STS, no loads in the loop
-    int32_t* wp = stage + loc;
-    walk_words<!HALF>(a, slot, cell, [&](uint32_t word, int32_t first) {
-      do {
-        const int b = __clz(word);
-        word &= ~(0x80000000u >> b);
-        *wp++ = first + b;
-      } while (word);
-    });
-  }
-  __syncthreads();
-  // copy-out: one warp per row, partner ids gathered 32 at a time, coalesced stores
-  for (int r = warp; r < EM_THREADS; r += EM_THREADS / 32) {
-    const int32_t n = s_len[r];
-    if (n == 0 && !(HALF && COUNT)) continue;
-    const int32_t* src = stage + s_loc[r];
+  int32_t fill = 0;  // entries staged in this lane's line
+  int32_t done = 0;  // entries of this row already written (HALF: after the id filter)
+
+  auto flush = [&]() {
+    __syncwarp();
     if (!HALF) {
-      int32_t* out = a.partners + s_dst[r];
-      for (int32_t t = lane; t < n; t += 32) {
-        int32_t pid = __ldg(a.sorted_ids + src[t]);
-        if (GID) pid = __ldg(a.global_ids + pid);
-        out[t] = pid;
-      }
-    } else {
-      int32_t rcmp = s_id[r];
-      if (COUNT && GID && rcmp < a.n_owned) rcmp = __ldg(a.global_ids + rcmp);
-      int32_t* out = a.partners + s_dst[r];
-      int32_t run = 0;
-      for (int32_t t0 = 0; t0 < n; t0 += 32) {
-        const int32_t t = t0 + lane;
-        int32_t pid = -2147483647 - 1;
-        if (t < n) {
-          pid = __ldg(a.sorted_ids + src[t]);
-          if (GID) pid = __ldg(a.global_ids + pid);
+      // four rows per step: their gathers are all in flight before the first store needs one
+      for (int r0 = 0; r0 < 32; r0 += 4) {
+        int32_t n[4], pid[4];
+        long long base[4];
+        int32_t nmax = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          n[j] = __shfl_sync(0xffffffffu, fill, r0 + j);
+          base[j] = __shfl_sync(0xffffffffu, dst + done, r0 + j);
+          nmax = max(nmax, n[j]);
         }
-        const bool keep = (t < n) && (pid > rcmp);
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (!COUNT && keep) out[run + __popc(bal & ((1u << lane) - 1u))] = pid;
-        run += __popc(bal);
+        for (int32_t t0 = 0; t0 < nmax; t0 += 32) {
+          const int32_t t = t0 + lane;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            pid[j] = 0;
+            if (t < n[j]) pid[j] = __ldg(a.sorted_ids + tile[(r0 + j) * EM_LINE + t]);
+          }
+          if (GID) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              if (t < n[j]) pid[j] = __ldg(a.global_ids + pid[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (t < n[j]) a.partners[base[j] + t] = pid[j];
+        }
       }
-      if (COUNT && lane == 0 && s_id[r] < a.n_owned) a.counts[s_id[r]] = run;
+      done += fill;
+    } else {
+      for (int r = 0; r < 32; r++) {
+        const int32_t n = __shfl_sync(0xffffffffu, fill, r);
+        if (n == 0) continue;
+        const long long base = __shfl_sync(0xffffffffu, dst + done, r);
+        const int32_t* src = tile + r * EM_LINE;
+        const int32_t rc = __shfl_sync(0xffffffffu, rcmp, r);
+        int32_t run = 0;
+        for (int32_t t0 = 0; t0 < n; t0 += 32) {
+          const int32_t t = t0 + lane;
+          int32_t pid = -2147483647 - 1;
+          if (t < n) {
+            pid = __ldg(a.sorted_ids + src[t]);
+            if (GID) pid = __ldg(a.global_ids + pid);
+          }
+          const bool keep = (t < n) && (pid > rc);
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          if (!COUNT && keep) a.partners[base + run + __popc(bal & ((1u << lane) - 1u))] = pid;
+          run += __popc(bal);
+        }
+        if (lane == r) done += run;
+      }
+    }
+    fill = 0;
+    __syncwarp();
+  };
+
+  const int32_t mx = a.mesh[0], my = a.mesh[1], mz = a.mesh[2];
+  const int32_t bx = cell % mx, by = (cell / mx) % my, bz = cell / (mx * my);
+  int xlo, xhi, ylo, yhi, zlo, zhi;
+  axis_range(bx, mx, xlo, xhi);
+  axis_range(by, my, ylo, yhi);
+  axis_range(bz, mz, zlo, zhi);
+  const int32_t nx = owned ? xhi - xlo + 1 : 0, ny = yhi - ylo + 1, nz = zhi - zlo + 1;
+  const int32_t own = owned ? slot - __ldg(a.cell_start + cell) : 0;
+  const uint32_t* mrow = a.mask + slot;
+  const bool two = a.wi >= 2;
+
+  // the plane / run loops are warp-uniform (3 x 3 stencil ordinals); lanes without that run see empty words
+  for (int oz = 0; oz < 3; oz++) {
+    // all loads of the plane (3 runs x (4 cell starts + 6 words)) are issued before any is used; the word loads do
+    // not wait for the cell starts (words beyond a cell's population are discarded afterwards)
+    int32_t cbp[3][4];
+    uint32_t mp[3][3][2];
+#pragma unroll
+    for (int oy = 0; oy < 3; oy++) {
+      const bool rv = (nx > 0) && (oz < nz) && (oy < ny);
+      const int32_t* cs = a.cell_start + ((ylo + oy) + (zlo + oz) * my) * mx + xlo;
+#pragma unroll
+      for (int k = 0; k < 4; k++) cbp[oy][k] = (rv && k <= nx) ? __ldg(cs + k) : 0;
+      const int32_t o0 = (oz * 3 + oy) * 3 * a.wi;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const bool cv = rv && k < nx;
+        mp[oy][k][0] = cv ? __ldg(mrow + (long long)(o0 + k * a.wi) * a.n_cap) : 0u;
+        mp[oy][k][1] = (cv && two) ? __ldg(mrow + (long long)(o0 + k * a.wi + 1) * a.n_cap) : 0u;
+      }
+    }
+#pragma unroll
+    for (int oy = 0; oy < 3; oy++) {
+      const bool rv = (nx > 0) && (oz < nz) && (oy < ny);
+      const int32_t o0 = (oz * 3 + oy) * 3 * a.wi;
+      int32_t cb[4], nw[3];
+      uint32_t m[3][2];
+#pragma unroll
+      for (int k = 0; k < 4; k++) cb[k] = cbp[oy][k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        nw[k] = (rv && k < nx) ? min((cb[k + 1] - cb[k] + 31) >> 5, a.wi) : 0;  // > wi only after FLAG_CELL_WORDS
+        m[k][0] = nw[k] > 0 ? mp[oy][k][0] : 0u;
+        m[k][1] = nw[k] > 1 ? mp[oy][k][1] : 0u;
+      }
+      const bool own_run = !HALF && rv && (zlo + oz == bz) && (ylo + oy == by);  // FULL: j != i
+      if (own_run) {
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int u = 0; u < 2; u++)
+            if (xlo + k == bx && (own >> 5) == u) m[k][u] &= ~(0x80000000u >> (own & 31));
+      }
+      int32_t pc[3][2], run_hits = 0;
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          pc[k][u] = __popc(m[k][u]);
+          run_hits += pc[k][u];
+        }
+      const bool slow_lane = max(nw[0], max(nw[1], nw[2])) > 2 || run_hits > EM_TILE;
+      if (__any_sync(0xffffffffu, fill + run_hits > EM_TILE)) flush();
+      if (!__any_sync(0xffffffffu, slow_lane)) {
+        int32_t* wp = line + fill;
+        fill += run_hits;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          // stencil order: cell 0 (words 0, 1), cell 1, cell 2
+          int32_t* q0 = wp + (u ? pc[0][0] : 0);
+          int32_t* q1 = wp + pc[0][0] + pc[0][1] + (u ? pc[1][0] : 0);
+          int32_t* q2 = wp + pc[0][0] + pc[0][1] + pc[1][0] + pc[1][1] + (u ? pc[2][0] : 0);
+          uint32_t w0 = m[0][u], w1 = m[1][u], w2 = m[2][u];
+          const int32_t f0 = cb[0] + 32 * u, f1 = cb[1] + 32 * u, f2 = cb[2] + 32 * u;
+          while (w0 | w1 | w2) {
+            if (w0) {
+              const int b = __clz(w0);
+              w0 &= ~(0x80000000u >> b);
+              *q0++ = f0 + b;
+            }
+            if (w1) {
+              const int b = __clz(w1);
+              w1 &= ~(0x80000000u >> b);
+              *q1++ = f1 + b;
+            }
+            if (w2) {
+              const int b = __clz(w2);
+              w2 &= ~(0x80000000u >> b);
+              *q2++ = f2 + b;
+            }
+          }
+        }
+      } else {
+        // a cell of this run holds more than 64 particles (or the run alone overflows a line): word by word,
+        // warp-uniform loop bounds, a flush check before every word
+        for (int k = 0; k < 3; k++)
+          for (int32_t w = 0; w < a.wi; w++) {
+            const int32_t nwk = k == 0 ? nw[0] : (k == 1 ? nw[1] : nw[2]);
+            uint32_t word = 0u;
+            if (w < nwk) {
+              word = __ldg(mrow + (long long)(o0 + k * a.wi + w) * a.n_cap);
+              if (own_run && xlo + k == bx && (own >> 5) == w) word &= ~(0x80000000u >> (own & 31));
+            }
+            if (!__any_sync(0xffffffffu, word != 0u)) continue;
+            if (__any_sync(0xffffffffu, fill + __popc(word) > EM_TILE)) flush();
+            const int32_t first = (k == 0 ? cb[0] : (k == 1 ? cb[1] : cb[2])) + 32 * w;
+            while (word) {
+              const int b = __clz(word);
+              word &= ~(0x80000000u >> b);
+              line[fill++] = first + b;
+            }
+          }
+      }
     }
   }
+  if (__any_sync(0xffffffffu, fill > 0)) flush();
+  if (COUNT && owned) a.counts[id] = done;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,3 @@
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest8.txt 2>&1; tail -5 gpurun_out/pytest8.txt
+python tools/bench_workload.py fcc 50 full_csr 7 > gpurun_out/wl_fcc50.txt 2>&1; tail -1 gpurun_out/wl_fcc50.txt
+python tools/bench_workload.py uniform 2097152 full_csr 5 > gpurun_out/wl_uni2m.txt 2>&1; tail -1 gpurun_out/wl_uni2m.txt
