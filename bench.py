@@ -330,16 +330,35 @@ def run_ours(args):
         n = n_owned
         # algorithmic bytes: B_alg = N*(V+8) + 4*P per build, V = 32 (double4)
         b_alg_build = n * (32 + 8) + 4 * entries_local
-        # the dominant kernel (search_fill) reads one 16-B record + one 8-B offset per particle, writes 4 B per entry
-        b_alg_fill = n * (16 + 8) + 4 * entries_local
-        fill_ms = stage_ms.get("search_fill")
-        roof = {"bound": "hbm", "kernel": "search_kernel<FILL>", "achieved": None, "peak": peak, "unit": "GB/s",
-                "frac": None, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": b_alg_fill}
-        if fill_ms:
-            roof["achieved"] = b_alg_fill / (fill_ms * 1e-3) / 1e9
+        # Dominant kernel = the longest stage of the profiled build.  Algorithmic bytes per launch:
+        #   emit_kernel      writes 4 B per list entry, reads 8 B offset + 4 B id per row      -> 4 P + 12 N
+        #   pairmask_kernel  reads one 16-B cell-sorted record per particle, writes nothing the algorithm asks for;
+        #                    it is bounded by FP32 issue (3 FFMA + 1 FADD per distance test), reported beside it
+        kern = {"emit": ("emit_kernel", 4 * entries_local + 12 * n),
+                "pairmask": ("pairmask_kernel", 16 * n),
+                "search_fill": ("search_kernel<FILL>", n * (16 + 8) + 4 * entries_local),
+                "search_count": ("search_kernel<COUNT>", n * (16 + 4))}
+        dom = max((k for k in stage_ms if k in kern), key=lambda k: stage_ms[k], default=None)
+        roof = {"bound": "hbm", "kernel": None, "achieved": None, "peak": peak, "unit": "GB/s",
+                "frac": None, "traffic": None, "peak_source": peak_src}
+        if dom:
+            name, b_alg_k = kern[dom]
+            roof.update({"kernel": name, "algorithmic_bytes_per_launch": b_alg_k, "kernel_ms": stage_ms[dom],
+                         "achieved": b_alg_k / (stage_ms[dom] * 1e-3) / 1e9})
             roof["frac"] = roof["achieved"] / peak
-            roof["kernel_ms"] = fill_ms
+            roof["kernel_share_of_build"] = stage_ms[dom] / max(sum(stage_ms.values()), 1e-12)
+        # ncu --set full capture of the same kernel (profiles/): dram__bytes_read.sum + dram__bytes_write.sum
+        traffic_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if dom and os.path.exists(traffic_file):
+            with open(traffic_file) as f:
+                roof["traffic"] = json.load(f).get(kern[dom][0])
+        if "pairmask" in stage_ms:
+            # secondary ceiling: the distance tests themselves, 4 FP32-pipe lane-ops each at the measured
+            # 126 lane-FMA/clk/SM (profiles/r01_microbench_issue_rates.txt)
+            t_fp32 = st.candidates_tested * 4 / (126.0 * 148 * 1.965e9) * 1e3
+            roof["fp32_issue_floor_ms_pairmask"] = t_fp32
+            roof["pairmask_ms"] = stage_ms["pairmask"]
+            roof["pairmask_frac_of_fp32_issue"] = t_fp32 / stage_ms["pairmask"]
         build_gbs = b_alg_build / (ms_step * 1e-3) / 1e9
         q_host_np = q
         cpu = None
@@ -353,7 +372,8 @@ def run_ours(args):
                              f"(the reference is single-threaded); ms/build: "
                              + ", ".join(f"{k}={v:.1f}" for k, v in times.items()),
                    "ms_per_build": times, "host_nproc": os.cpu_count()}
-        kernels_per_build = 7
+        # kernels of one build: bin, scan(cells), scatter, cellsort, pairmask, rowcount, scan(counts), emit
+        kernels_per_build = 8
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -368,7 +388,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "build": {"ms_cold_l2": ms_step, "ms_hot_l2_back_to_back": ms_hot,
                       "entries_per_s": entries_all / (ms_step * 1e-3),
-                      "candidate_tests_per_s": st.candidates_tested * 2 / (ms_step * 1e-3),
+                      "candidate_tests_per_s": st.candidates_tested / (ms_step * 1e-3),
                       "candidates_per_pass": st.candidates_tested, "band_retests": st.band_tests,
                       "algorithmic_bytes": b_alg_build, "algorithmic_gbs": build_gbs,
                       "frac_of_hbm_peak": build_gbs / peak, "stage_ms": stage_ms,

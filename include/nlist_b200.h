@@ -155,6 +155,9 @@ int nlb200_build_host(nlb200_handle h, const void* q_host, int64_t n, int32_t* n
                       int64_t* offsets_host, int32_t* partners_host, int64_t partners_capacity,
                       int64_t* number_of_pairs);
 
+/* D2H copy of the partner list of the last synchronized build into partners_host (capacity entries). */
+int nlb200_fetch_partners_host(nlb200_handle h, int32_t* partners_host, int64_t capacity);
+
 /* ---- accessors (borrowed device pointers) --------------------------------------------------------------------- */
 
 /* number_of_partners() — neighlist_gpu.hpp:476-482, neighlist_cpu.hpp:455-461.  int32[n]. */

@@ -41,6 +41,7 @@ SYMBOLS = {
     "nlb200_build_subset": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "nlb200_synchronize": (C.c_int, [_vp]),
     "nlb200_build_host": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
+    "nlb200_fetch_partners_host": (C.c_int, [_vp, _vp, _i64]),
     "nlb200_number_of_partners": (_vp, [_vp]),
     "nlb200_offsets": (_vp, [_vp]),
     "nlb200_offsets32": (_vp, [_vp]),

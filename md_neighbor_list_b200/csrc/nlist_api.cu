@@ -818,6 +818,17 @@ int nlb200_build_host(nlb200_handle h, const void* q_host, int64_t n, int32_t* n
   return NLB200_OK;
 }
 
+int nlb200_fetch_partners_host(nlb200_handle h, int32_t* partners_host, int64_t capacity) {
+  if (!h) return NLB200_ERR_INVALID;
+  if (!h->have_result) return fail(h, NLB200_ERR_STATE, "no synchronized build to fetch");
+  const int64_t total = h->stats.number_of_pairs;
+  if (total > capacity || (total > 0 && !partners_host))
+    return fail(h, NLB200_ERR_CAPACITY, "host partner buffer holds %lld entries, %lld needed", (long long)capacity,
+                (long long)total);
+  if (total) CK(h, cudaMemcpy(partners_host, h->partners, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost));
+  return NLB200_OK;
+}
+
 const int32_t* nlb200_number_of_partners(nlb200_handle h) { return h ? h->counts : nullptr; }
 const int64_t* nlb200_offsets(nlb200_handle h) { return h ? h->offsets : nullptr; }
 const int32_t* nlb200_offsets32(nlb200_handle h) {

@@ -532,15 +532,40 @@ __global__ void __launch_bounds__(128) search_kernel(SearchArgs<T> a) {
 //   Rows come out in stencil order: cells ascending, ids ascending inside a cell — the discovery order of the
 //   reference kernels (kernel_impl.cuh:17-33).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int PM_RJ = 4;         // candidates per lane
+#ifndef NLB_PM_RJ
+#define NLB_PM_RJ 8
+#endif
+constexpr int PM_RJ = NLB_PM_RJ;  // candidates per lane (packed in pairs)
 constexpr int PM_THREADS = 128;  // 4 warps per cell
 constexpr uint32_t FLAG_CELL_WORDS = 16u;  // a cell holds more than 32*WI particles: mask words too narrow
 
 __device__ __forceinline__ int axis_lo(int c, int m) { return m == 3 ? 0 : max(c - 1, 0); }
 
-// (SL^2 - r^2)/2 in FP32, fixed evaluation order (recomputed bit-identically by the band re-test)
-__device__ __forceinline__ float pre_d(const float4& p, float xj, float yj, float zj, float wj) {
-  return __fsub_rn(__fmaf_rn(p.x, xj, __fmaf_rn(p.y, yj, __fmaf_rn(p.z, zj, wj))), p.w);
+// (SL^2 - r^2)/2 in FP32, fixed evaluation order: d = fma(xi, xj, fma(yi, yj, fma(zi, zj, wj))) + nai, nai = -ai.
+// The hot loop evaluates two candidates per instruction with the packed forms (FFMA2 / FADD2: IEEE per element, so
+// the scalar form below — used by the band re-test — reproduces the same bits).
+__device__ __forceinline__ float pre_d(float xi, float yi, float zi, float nai, float xj, float yj, float zj,
+                                       float wj) {
+  return __fadd_rn(__fmaf_rn(xi, xj, __fmaf_rn(yi, yj, __fmaf_rn(zi, zj, wj))), nai);
+}
+typedef unsigned long long f32x2;  // two floats in one 64-bit register pair
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
 }
 
 template <typename T>
@@ -564,15 +589,19 @@ struct PairMaskArgs {
 
 // per-warp shared memory: the cell's particles + its run table
 constexpr int PM_TAB = 64;  // ints: start[9] b1[9] b2[9] pre[10] o[9] ty[9] tz[9]
-__host__ __device__ inline size_t pm_warp_bytes(int wi) { return (size_t)wi * 32 * sizeof(float4) + PM_TAB * 4; }
+// particles are stored pre-duplicated for the packed FMAs: {xi, xi, yi, yi}, {zi, zi, -ai, -ai}
+__host__ __device__ inline size_t pm_warp_bytes(int wi) { return (size_t)wi * 32 * 2 * sizeof(float4) + PM_TAB * 4; }
 
+#ifndef NLB_PM_MINB
+#define NLB_PM_MINB 1
+#endif
 template <typename T, int STRIDE>
-__global__ void __launch_bounds__(PM_THREADS) pairmask_kernel(PairMaskArgs<T> a) {
+__global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairMaskArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   unsigned char* wbase = smem_raw + (size_t)warp * pm_warp_bytes(a.wi);
-  float4* si = reinterpret_cast<float4*>(wbase);  // [32 * wi]
-  int32_t* t_start = reinterpret_cast<int32_t*>(wbase + (size_t)a.wi * 32 * sizeof(float4));
+  float4* si = reinterpret_cast<float4*>(wbase);  // [32 * wi][2]
+  int32_t* t_start = reinterpret_cast<int32_t*>(wbase + (size_t)a.wi * 32 * 2 * sizeof(float4));
   int32_t* t_b1 = t_start + 9;
   int32_t* t_b2 = t_b1 + 9;
   int32_t* t_pre = t_b2 + 9;  // [10]
@@ -645,17 +674,24 @@ __global__ void __launch_bounds__(PM_THREADS) pairmask_kernel(PairMaskArgs<T> a)
       for (int32_t k = lane; k < ni; k += 32) {
         const float4 r = __ldg(a.rec + ibeg + k);
         const float x = r.x - hx, y = r.y - hy, z = r.z - hz;
-        si[k] = make_float4(x, y, z, 0.5f * (fmaf(x, x, fmaf(y, y, z * z)) - gp.sl2f));
+        const float nai = -0.5f * (fmaf(x, x, fmaf(y, y, z * z)) - gp.sl2f);
+        si[2 * k] = make_float4(x, x, y, y);
+        si[2 * k + 1] = make_float4(z, z, nai, nai);
       }
       __syncwarp();
       const int32_t nj = t_pre[9];
       if (lane == 0 && part == 0) cand_local += (unsigned long long)ni * (unsigned long long)nj;
       const float tx0 = (float)(xlo - cx) - 0.5f;
 
+      // ordinal (x part) of this cell inside the stencil of a candidate in column xlo + col
+      int32_t oxs[3];
+#pragma unroll
+      for (int col = 0; col < 3; col++) oxs[col] = cx - axis_lo(min(xlo + col, mx - 1), mx);
+
       for (int32_t c0 = part * (32 * PM_RJ); c0 < nj; c0 += a.parts * (32 * PM_RJ)) {
         float xj[PM_RJ], yj[PM_RJ], zj[PM_RJ], wj[PM_RJ];
-        int32_t sj[PM_RJ];    // candidate's slot
-        uint32_t* mp[PM_RJ];  // its mask word for this cell (nullptr: tail lane or ghost row)
+        int32_t sj[PM_RJ];  // candidate's slot
+        int32_t oj[PM_RJ];  // its mask plane for this cell (o * wi); -1: tail lane or ghost row, nothing to store
         int r = 0;
 #pragma unroll
         for (int k = 0; k < PM_RJ; k++) {
@@ -663,7 +699,7 @@ __global__ void __launch_bounds__(PM_THREADS) pairmask_kernel(PairMaskArgs<T> a)
           xj[k] = yj[k] = zj[k] = 0.f;
           wj[k] = -1.0e30f;  // d = -1e30: a miss, far from the band
           sj[k] = 0;
-          mp[k] = nullptr;
+          oj[k] = -1;
           if (c < nj) {
             while (c >= t_pre[r + 1]) r++;
             const int32_t s = t_start[r] + (c - t_pre[r]);
@@ -676,57 +712,90 @@ __global__ void __launch_bounds__(PM_THREADS) pairmask_kernel(PairMaskArgs<T> a)
             sj[k] = s;
             bool store = true;
             if (a.has_ghosts) store = __ldg(a.sorted_ids + s) < a.n_owned;
-            if (store) {
-              const int32_t o = t_o[r] + (cx - axis_lo(xlo + col, mx));
-              mp[k] = a.mask + (long long)(o * a.wi) * a.n_cap + s;
-            }
+            if (store) oj[k] = (t_o[r] + (col == 0 ? oxs[0] : (col == 1 ? oxs[1] : oxs[2]))) * a.wi;
           }
+        }
+        f32x2 X[PM_RJ / 2], Y[PM_RJ / 2], Z[PM_RJ / 2], W[PM_RJ / 2];
+#pragma unroll
+        for (int h = 0; h < PM_RJ / 2; h++) {
+          X[h] = pack2(xj[2 * h], xj[2 * h + 1]);
+          Y[h] = pack2(yj[2 * h], yj[2 * h + 1]);
+          Z[h] = pack2(zj[2 * h], zj[2 * h + 1]);
+          W[h] = pack2(wj[2 * h], wj[2 * h + 1]);
         }
         for (int32_t w = 0; w * 32 < ni; w++) {
           const int32_t cnt = min(32, ni - w * 32);
-          const float4* sp = si + w * 32;
+          const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(si + w * 64);
           uint32_t miss[PM_RJ];
 #pragma unroll
           for (int k = 0; k < PM_RJ; k++) miss[k] = 0u;
-          float m = 3.0e38f;
-#pragma unroll 4
-          for (int32_t ii = 0; ii < cnt; ii++) {
-            const float4 p = sp[ii];
+          float mh[PM_RJ / 2];  // min |d| per candidate pair
 #pragma unroll
-            for (int k = 0; k < PM_RJ; k++) {
-              const float d = pre_d(p, xj[k], yj[k], zj[k], wj[k]);
-              miss[k] = __funnelshift_l(__float_as_uint(d), miss[k], 1);  // shift the sign bit in
-              m = fminf(m, fabsf(d));
+          for (int h = 0; h < PM_RJ / 2; h++) mh[h] = 3.0e38f;
+#pragma unroll 2
+          for (int32_t ii = 0; ii < cnt; ii++) {
+            const ulonglong2 p0 = sp[2 * ii];      // {xi, xi}, {yi, yi}
+            const ulonglong2 p1 = sp[2 * ii + 1];  // {zi, zi}, {-ai, -ai}
+#pragma unroll
+            for (int h = 0; h < PM_RJ / 2; h++) {
+              const f32x2 d2 = add2(fma2(p0.x, X[h], fma2(p0.y, Y[h], fma2(p1.x, Z[h], W[h]))), p1.y);
+              float d0, d1;
+              unpack2(d2, d0, d1);
+              miss[2 * h] = __funnelshift_l(__float_as_uint(d0), miss[2 * h], 1);  // shift the sign bit in
+              miss[2 * h + 1] = __funnelshift_l(__float_as_uint(d1), miss[2 * h + 1], 1);
+              mh[h] = fminf(mh[h], fminf(fabsf(d0), fabsf(d1)));
             }
           }
           uint32_t hits[PM_RJ];
 #pragma unroll
           for (int k = 0; k < PM_RJ; k++) hits[k] = (~miss[k]) << (32 - cnt);  // bit (31 - ii) <-> particle w*32+ii
-          if (m < a.band) {
-            // some test of this word fell inside the pre-filter's uncertainty band: decide those exactly (rare)
+          // Tests that fell inside the pre-filter's uncertainty band are decided exactly, in the caller's precision.
+          // Rare per test (~2e-5) but not per word (8192 tests): the re-check is done by the whole warp — lane = particle
+          // ii, the triggering lane's candidate broadcast by shuffles — instead of one lane looping alone.
+          float mall = mh[0];
 #pragma unroll
-            for (int k = 0; k < PM_RJ; k++) {
-              if (mp[k] == nullptr) continue;
-              for (int32_t ii = 0; ii < cnt; ii++) {
-                const float d = pre_d(sp[ii], xj[k], yj[k], zj[k], wj[k]);
-                if (fabsf(d) < a.band) {
-                  const int32_t iid = __ldg(a.sorted_ids + ibeg + w * 32 + ii);
-                  const int32_t jid = __ldg(a.sorted_ids + sj[k]);
-                  const bool hit =
-                      exact_within(load_pos<T, STRIDE>(a.q, iid), load_pos<T, STRIDE>(a.q, jid), gp.sl2);
-                  const uint32_t bit = 0x80000000u >> ii;
-                  hits[k] = hit ? (hits[k] | bit) : (hits[k] & ~bit);
-                  band_local++;
+          for (int h = 1; h < PM_RJ / 2; h++) mall = fminf(mall, mh[h]);
+          unsigned trig = __ballot_sync(0xffffffffu, mall < a.band);
+          while (trig) {
+            const int src = __ffs(trig) - 1;
+            trig &= trig - 1;
+#pragma unroll
+            for (int h = 0; h < PM_RJ / 2; h++) {
+              if (!(__shfl_sync(0xffffffffu, mh[h], src) < a.band)) continue;  // warp-uniform
+              const f32x2 xs = __shfl_sync(0xffffffffu, X[h], src), ys = __shfl_sync(0xffffffffu, Y[h], src);
+              const f32x2 zs = __shfl_sync(0xffffffffu, Z[h], src), ws = __shfl_sync(0xffffffffu, W[h], src);
+              float cx2[2], cy2[2], cz2[2], cw2[2];
+              unpack2(xs, cx2[0], cx2[1]);
+              unpack2(ys, cy2[0], cy2[1]);
+              unpack2(zs, cz2[0], cz2[1]);
+              unpack2(ws, cw2[0], cw2[1]);
+#pragma unroll
+              for (int e = 0; e < 2; e++) {
+                const int k = 2 * h + e;
+                const int32_t s_src = __shfl_sync(0xffffffffu, sj[k], src);
+                const int32_t o_src = __shfl_sync(0xffffffffu, oj[k], src);
+                bool fix = false, hit = false;
+                if (lane < cnt && o_src >= 0) {
+                  const float4 q0 = si[w * 64 + 2 * lane], q1 = si[w * 64 + 2 * lane + 1];
+                  const float d = pre_d(q0.x, q0.z, q1.x, q1.z, cx2[e], cy2[e], cz2[e], cw2[e]);
+                  if (fabsf(d) < a.band) {
+                    const int32_t iid = __ldg(a.sorted_ids + ibeg + w * 32 + lane);
+                    const int32_t jid = __ldg(a.sorted_ids + s_src);
+                    hit = exact_within(load_pos<T, STRIDE>(a.q, iid), load_pos<T, STRIDE>(a.q, jid), gp.sl2);
+                    fix = true;
+                    band_local++;
+                  }
                 }
+                // lane ii <-> bit (31 - ii)
+                const uint32_t fixm = __brev(__ballot_sync(0xffffffffu, fix));
+                const uint32_t hitm = __brev(__ballot_sync(0xffffffffu, hit));
+                if (lane == src) hits[k] = (hits[k] & ~fixm) | hitm;
               }
             }
           }
 #pragma unroll
           for (int k = 0; k < PM_RJ; k++)
-            if (mp[k] != nullptr) {
-              *mp[k] = hits[k];
-              mp[k] += a.n_cap;
-            }
+            if (oj[k] >= 0) a.mask[(long long)(oj[k] + w) * a.n_cap + sj[k]] = hits[k];
         }
       }
     }
@@ -836,6 +905,7 @@ __global__ void __launch_bounds__(EM_WARPS * 32) emit_kernel(EmitArgs a) {
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   int32_t* tile = em_smem + warp * 32 * EM_LINE;
   int32_t* line = tile + lane * EM_LINE;
+  const uint32_t line_sa = (uint32_t)__cvta_generic_to_shared(line);
   const int32_t slot = (blockIdx.x * EM_WARPS + warp) * 32 + lane;
   int32_t id = 0x7fffffff;
   if (slot < a.n_total) id = __ldg(a.sorted_ids + slot);
@@ -958,42 +1028,29 @@ __global__ void __launch_bounds__(EM_WARPS * 32) emit_kernel(EmitArgs a) {
           for (int u = 0; u < 2; u++)
             if (xlo + k == bx && (own >> 5) == u) m[k][u] &= ~(0x80000000u >> (own & 31));
       }
-      int32_t pc[3][2], run_hits = 0;
+      int32_t run_hits = 0;
 #pragma unroll
       for (int k = 0; k < 3; k++)
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
-          pc[k][u] = __popc(m[k][u]);
-          run_hits += pc[k][u];
-        }
+        for (int u = 0; u < 2; u++) run_hits += __popc(m[k][u]);
       const bool slow_lane = max(nw[0], max(nw[1], nw[2])) > 2 || run_hits > EM_TILE;
       if (__any_sync(0xffffffffu, fill + run_hits > EM_TILE)) flush();
       if (!__any_sync(0xffffffffu, slow_lane)) {
-        int32_t* wp = line + fill;
+        // stencil order: cell 0 (words 0, 1), cell 1, cell 2; lanes of a warp sit in the same or adjacent cells, so
+        // their popcounts of one word are alike and the per-word loops stay reasonably full
+        uint32_t wa = line_sa + 4u * (uint32_t)fill;  // shared-memory byte address of the next free entry
         fill += run_hits;
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
-          // stencil order: cell 0 (words 0, 1), cell 1, cell 2
-          int32_t* q0 = wp + (u ? pc[0][0] : 0);
-          int32_t* q1 = wp + pc[0][0] + pc[0][1] + (u ? pc[1][0] : 0);
-          int32_t* q2 = wp + pc[0][0] + pc[0][1] + pc[1][0] + pc[1][1] + (u ? pc[2][0] : 0);
-          uint32_t w0 = m[0][u], w1 = m[1][u], w2 = m[2][u];
-          const int32_t f0 = cb[0] + 32 * u, f1 = cb[1] + 32 * u, f2 = cb[2] + 32 * u;
-          while (w0 | w1 | w2) {
-            if (w0) {
-              const int b = __clz(w0);
-              w0 &= ~(0x80000000u >> b);
-              *q0++ = f0 + b;
-            }
-            if (w1) {
-              const int b = __clz(w1);
-              w1 &= ~(0x80000000u >> b);
-              *q1++ = f1 + b;
-            }
-            if (w2) {
-              const int b = __clz(w2);
-              w2 &= ~(0x80000000u >> b);
-              *q2++ = f2 + b;
+        for (int k = 0; k < 3; k++) {
+#pragma unroll
+          for (int u = 0; u < 2; u++) {
+            uint32_t word = m[k][u];
+            const int32_t first = cb[k] + 32 * u;
+            while (word) {
+              const int b = __clz(word);
+              word &= ~(0x80000000u >> b);
+              asm volatile("st.shared.s32 [%0], %1;" ::"r"(wa), "r"(first + b) : "memory");
+              wa += 4u;
             }
           }
         }

@@ -1,0 +1,109 @@
+"""Multi-process logic of the slab decomposition (md_neighbor_list_b200/parallel.py) on CPU: world_size 2 and 3 over
+the gloo backend.  Partition, ghost selection, exchange and the ownership rule are the product code; the list build
+itself is replaced by the oracle (tests may call it), so that no GPU is needed.  The union of the ranks' rows must be
+exactly the single-process list of the global system, FULL and HALF."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+SL = 3.3
+
+
+def _free_port() -> int:
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _global_system(world: int):
+    from oracle import oracle as O
+    L = 16.0
+    s = (0.25 * 1.0) ** (-1.0 / 3.0)
+    sx = int(L / s)
+    q = O.gen_fcc(1.0, L, sx, sx, sx * world)
+    return q, (L, L, L * world)
+
+
+def _rows(csr, rows_of, mapping):
+    out = []
+    for i in rows_of:
+        b, e = csr.offsets[i], csr.offsets[i + 1]
+        out.append(np.sort(mapping[csr.partners[b:e]]))
+    return out
+
+
+def _worker(rank: int, world: int, port: int):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from md_neighbor_list_b200.parallel import SlabDecomposition
+        from oracle import oracle as O
+        q, box = _global_system(world)
+        ref_full = O.build_full(q, SL, box)
+        dec = SlabDecomposition(world, rank, box, SL, axis=2)
+        q_own, gid_own = dec.partition(q)
+        assert q_own.shape[0] > 0
+
+        def build_fn(q_all, n_owned, gid_all):
+            qa = q_all.numpy()
+            ga = gid_all.numpy()
+            # ghosts must be exactly the foreign particles within SL of this slab's faces
+            lo, hi = rank * dec.thickness, (rank + 1) * dec.thickness
+            z = q[:, 2]
+            want = set()
+            if rank > 0:
+                want |= set(np.nonzero((z < lo) & (z >= lo - SL))[0].tolist())
+            if rank + 1 < world:
+                want |= set(np.nonzero((z >= hi) & (z < hi + SL))[0].tolist())
+            assert set(ga[n_owned:].tolist()) == want
+            assert np.array_equal(qa[n_owned:], q[ga[n_owned:]])
+            local = O.build_full(qa, SL, box)
+            return _rows(local, range(n_owned), ga), ga[:n_owned]
+
+        rows, gids = dec.build(None, torch.from_numpy(q_own), gid_owned=torch.from_numpy(gid_own), build_fn=build_fn)
+        ident = np.arange(q.shape[0])
+        want_rows = _rows(ref_full, gids, ident)
+        assert len(rows) == len(want_rows)
+        for a, b in zip(rows, want_rows):
+            assert np.array_equal(a, b)
+        # HALF ownership rule: the row of the smaller global id keeps the pair -> every pair exactly once
+        half_local = sum(int((r > g).sum()) for r, g in zip(rows, gids))
+        tot = torch.tensor([half_local], dtype=torch.int64)
+        dist.all_reduce(tot)
+        assert int(tot) == O.build_half(q, SL, box).number_of_pairs
+        # every particle is owned by exactly one rank
+        cnt = torch.tensor([q_own.shape[0]], dtype=torch.int64)
+        dist.all_reduce(cnt)
+        assert int(cnt) == q.shape[0]
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_decomposition_matches_single_process(world):
+    from oracle import oracle as O
+    O.lib()
+    mp.spawn(_worker, args=(world, _free_port()), nprocs=world, join=True)
+
+
+def test_slab_thinner_than_search_length_is_rejected():
+    from md_neighbor_list_b200.parallel import SlabDecomposition
+    with pytest.raises(ValueError):
+        SlabDecomposition(4, 0, (50.0, 50.0, 10.0), SL)
+
+
+def test_single_rank_is_a_no_op():
+    from md_neighbor_list_b200.parallel import SlabDecomposition
+    dec = SlabDecomposition(1, 0, (20.0, 20.0, 20.0), SL)
+    q = torch.rand(100, 4, dtype=torch.float64) * 20
+    g = torch.arange(100, dtype=torch.int32)
+    qa, ga, n = dec.exchange(q, g)
+    assert n == 100 and qa is q and ga is g and dec.max_ghosts(100) == 0
