@@ -42,6 +42,7 @@ struct nlb200_context {
   DeviceStatus* status_dev = nullptr;
   int32_t* queue = nullptr;  // work counter of the persistent pair-mask kernel (inside zero_region)
   int sm_count = 148;
+  int64_t l2_bytes = 0;
   int32_t* cell_start = nullptr;
   int2* cell_rank = nullptr;
   int32_t* perm = nullptr;
@@ -212,20 +213,24 @@ cudaError_t set_attr_ts() {
 constexpr int MAX_EMIT_SMEM = 200 * 1024;
 
 template <bool HALF, bool GID, bool COUNT>
-cudaError_t launch_emit_t(const EmitArgs& a, cudaStream_t s) {
-  constexpr int rows = EM_WARPS * 32;
-  emit_kernel<HALF, GID, COUNT><<<(unsigned)((a.n_total + rows - 1) / rows), rows,
-                                  (size_t)EM_WARPS * 32 * EM_LINE * sizeof(int32_t), s>>>(a);
+cudaError_t launch_emit_t(bool direct, const EmitArgs& a, cudaStream_t s) {
+  if (direct) {
+    emit_direct_kernel<HALF, GID, COUNT><<<(unsigned)((a.n_total + 127) / 128), 128, 0, s>>>(a);
+  } else {
+    constexpr int rows = EM_WARPS * 32;
+    emit_kernel<HALF, GID, COUNT><<<(unsigned)((a.n_total + rows - 1) / rows), rows,
+                                    (size_t)EM_WARPS * 32 * EM_LINE * sizeof(int32_t), s>>>(a);
+  }
   return cudaGetLastError();
 }
-cudaError_t launch_emit(bool half, bool count, const EmitArgs& a, cudaStream_t s) {
+cudaError_t launch_emit(bool half, bool count, bool direct, const EmitArgs& a, cudaStream_t s) {
   const bool gid = a.global_ids != nullptr;
   if (!half) {
     if (count) return cudaSuccess;  // FULL: the popcount pass already wrote counts[]
-    return gid ? launch_emit_t<false, true, false>(a, s) : launch_emit_t<false, false, false>(a, s);
+    return gid ? launch_emit_t<false, true, false>(direct, a, s) : launch_emit_t<false, false, false>(direct, a, s);
   }
-  if (count) return gid ? launch_emit_t<true, true, true>(a, s) : launch_emit_t<true, false, true>(a, s);
-  return gid ? launch_emit_t<true, true, false>(a, s) : launch_emit_t<true, false, false>(a, s);
+  if (count) return gid ? launch_emit_t<true, true, true>(direct, a, s) : launch_emit_t<true, false, true>(direct, a, s);
+  return gid ? launch_emit_t<true, true, false>(direct, a, s) : launch_emit_t<true, false, false>(direct, a, s);
 }
 
 template <bool HALF, bool GID, bool COUNT>
@@ -283,6 +288,8 @@ template <>
 const GridParams<float>& grid_of<float>(const nlb200_context* h) {
   return h->gp32;
 }
+
+int64_t estimate_entries(const nlb200_context* h, int64_t n);
 
 // Enqueue one build on `s` (plain launches; the caller may be capturing them into a graph).
 template <typename T, int STRIDE>
@@ -393,6 +400,7 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     em.offsets = h->offsets;
     em.partners = h->partners;
     em.capacity = h->cap_entries;
+    const bool direct = h->variant == 3;  // ablation: per-thread scalar stores instead of the staged emission
     CK(h, stage(ST_PAIRMASK));
     if (n > 0) {
       // persistent warps: as many CTAs as are resident at once, each warp draws cells from the queue
@@ -416,7 +424,7 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     CK(h, stage(ST_ROWCOUNT));
     if (n > 0) {
       if (half) {
-        CK(h, launch_emit(true, true, em, s));
+        CK(h, launch_emit(true, true, direct, em, s));  // HALF rows need the ids to count
       } else {
         rowcount_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(em);
         CK(h, cudaGetLastError());
@@ -431,7 +439,7 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
       CK(h, cudaGetLastError());
     }
     CK(h, stage(ST_EMIT));
-    if (n > 0) CK(h, launch_emit(half, false, em, s));
+    if (n > 0) CK(h, launch_emit(half, false, direct, em, s));
   }
   if (h->sort_rows) CK(h, stage(ST_SORT_ROWS));
   if (h->sort_rows && n_owned > 0) {
@@ -606,6 +614,11 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
   h->status_dev = reinterpret_cast<DeviceStatus*>(h->zero_region + o_st);
   h->queue = reinterpret_cast<int32_t*>(h->zero_region + o_q);
   CK(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
+  {
+    int l2 = 0;
+    CK(h, cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device));
+    h->l2_bytes = l2;
+  }
   CK(h, cudaMalloc(&h->cell_start, sizeof(int32_t) * (size_t)(M + 1)));
   CK(h, cudaMalloc(&h->cell_rank, sizeof(int2) * (size_t)n));
   CK(h, cudaMalloc(&h->perm, sizeof(int32_t) * (size_t)n));

@@ -49,6 +49,7 @@ class SlabDecomposition:
         self.group = group
         self._buf = None  # device workspaces, allocated on first build
         self._qall = self._gall = None
+        self._last = None
         self.last_counts = (0, 0, 0, 0)  # sent below, sent above, received from below, received from above
 
     # -- partitioning ---------------------------------------------------------------------------------------------
@@ -164,7 +165,13 @@ class SlabDecomposition:
         self.last_counts = (send[below][0].shape[0] if below in send else 0,
                             send[above][0].shape[0] if above in send else 0,
                             n_in.get(below, 0), n_in.get(above, 0))
-        return self._qall[:n_total], self._gall[:n_total], n
+        self._last = (self._qall[:n_total], self._gall[:n_total], n)
+        return self._last
+
+    def last_assembled(self):
+        """(q_all, gid_all, n_owned) of the last exchange — lets one rank rebuild (e.g. under a profiler) without a new
+        exchange, which would need every rank."""
+        return self._last
 
     # -- build ----------------------------------------------------------------------------------------------------
     def global_ids(self, n_owned: int, device) -> torch.Tensor:
