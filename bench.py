@@ -216,6 +216,8 @@ def run_ours(args):
         for _ in range(max(args.warmup, 3)):
             one_build()
     st = nl.synchronize()
+    if halo is not None:
+        halo.check()  # ghost-capacity overflow would have dropped ghosts
     pairs_local = st.number_of_pairs // 2
     entries_local = st.number_of_pairs
 

@@ -140,7 +140,8 @@ int nlb200_build(nlb200_handle h, const void* q_dev, int64_t n, void* stream);
 
 /* Multi-GPU form (no reference counterpart): q_dev holds n_total = owned + ghost records, rows are
  * emitted only for the first n_owned; if global_ids_dev != NULL partner ids (and the HALF-mode j > i rule) use
- * global_ids_dev[local index] instead of the local index. */
+ * global_ids_dev[local index] instead of the local index.  Ghost records (index >= n_owned) whose x is NaN are absent:
+ * padding of fixed-capacity halo buffers (nlb200_pack_slab). */
 int nlb200_build_subset(nlb200_handle h, const void* q_dev, int64_t n_total, int64_t n_owned,
                         const int32_t* global_ids_dev, void* stream);
 
@@ -201,7 +202,17 @@ int nlb200_select_slab(const void* q_dev, int64_t n, int dtype, int stride, int 
                        int32_t* out_idx_dev, int64_t capacity, int64_t* out_count_dev, void* workspace_dev,
                        int64_t workspace_bytes, void* stream);
 
-/* Bytes of workspace nlb200_select_slab needs for n particles. */
+/* Fixed-capacity halo packing (multi-GPU build without host synchronisation): the records of q with
+ * lo <= q[i][axis] < hi go to out_q_dev[0..count) (ascending i) with their global ids (gids_dev[i], or gid_base + i when
+ * gids_dev is NULL) in out_gid_dev; the remaining slots up to `capacity` are filled with NaN records.  A ghost record
+ * whose x is NaN is ABSENT for nlb200_build_subset: it is binned nowhere and appears in no row, so both sides of an
+ * exchange can always move `capacity` records.  *out_count_dev receives the true count (> capacity = overflow).
+ * Workspace as for nlb200_select_slab. */
+int nlb200_pack_slab(const void* q_dev, const int32_t* gids_dev, int32_t gid_base, int64_t n, int dtype, int stride,
+                     int axis, double lo, double hi, void* out_q_dev, int32_t* out_gid_dev, int64_t capacity,
+                     int64_t* out_count_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* Bytes of workspace nlb200_select_slab / nlb200_pack_slab need for n particles. */
 int64_t nlb200_select_slab_workspace(int64_t n);
 
 /* Gathers position records: dst[k] = src[idx[k]] (stride elements each). */

@@ -309,7 +309,8 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
   CK(h, cudaMemsetAsync(h->zero_region, 0, h->zero_bytes, s));
   CK(h, stage(ST_BIN));
   if (n > 0) {
-    bin_kernel<T, STRIDE><<<(n + 255) / 256, 256, 0, s>>>(q, n, gp, h->cell_count, h->cell_rank, h->status_dev);
+    bin_kernel<T, STRIDE><<<(n + 255) / 256, 256, 0, s>>>(q, n, (int32_t)n_owned, gp, h->cell_count, h->cell_rank,
+                                                          h->status_dev);
     CK(h, cudaGetLastError());
   }
   CK(h, stage(ST_SCAN_CELLS));
@@ -393,6 +394,7 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     for (int d = 0; d < 3; d++) em.mesh[d] = gp.mesh[d];
     em.n_total = n;
     em.n_owned = (int32_t)n_owned;
+    em.n_cells = M;
     em.mask = h->mask;
     em.n_cap = h->mask_ncap;
     em.wi = h->mask_wi;
@@ -922,6 +924,45 @@ int nlb200_select_slab(const void* q_dev, int64_t n, int dtype, int stride, int 
   scan_kernel<int64_t><<<(unsigned)(tiles - 1 > 0 ? tiles - 1 : 1), SCAN_THREADS, 0, s>>>(flags, n, pos, nullptr, state,
                                                                                          nullptr, nullptr, 0);
   slab_compact_kernel<<<g > 0 ? g : 1, 256, 0, s>>>(flags, pos, n, out_idx_dev, capacity, out_count_dev);
+  return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
+}
+
+int nlb200_pack_slab(const void* q_dev, const int32_t* gids_dev, int32_t gid_base, int64_t n, int dtype, int stride,
+                     int axis, double lo, double hi, void* out_q_dev, int32_t* out_gid_dev, int64_t capacity,
+                     int64_t* out_count_dev, void* workspace_dev, int64_t workspace_bytes, void* stream) {
+  if (n < 0 || capacity < 0 || axis < 0 || axis > 2 || (stride != 3 && stride != 4)) return NLB200_ERR_INVALID;
+  const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE + 1;
+  const size_t o_pos = align_up(sizeof(int32_t) * (size_t)(n + 8), 256);
+  const size_t o_state = align_up(o_pos + sizeof(int64_t) * (size_t)(n + 1), 256);
+  const size_t need = o_state + sizeof(unsigned long long) * (size_t)(tiles + 2);
+  if (workspace_dev == nullptr || (size_t)workspace_bytes < need) return NLB200_ERR_CAPACITY;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace_dev);
+  int32_t* flags = reinterpret_cast<int32_t*>(ws);
+  int64_t* pos = reinterpret_cast<int64_t*>(ws + o_pos);
+  unsigned long long* state = reinterpret_cast<unsigned long long*>(ws + o_state);
+  const size_t esz = dtype == NLB200_F64 ? 8 : 4;
+  // all-ones bytes are a NaN in both precisions: every slot starts as an absent ghost
+  if (capacity > 0 && cudaMemsetAsync(out_q_dev, 0xFF, (size_t)capacity * stride * esz, s) != cudaSuccess)
+    return NLB200_ERR_CUDA;
+  if (cudaMemsetAsync(state, 0, sizeof(unsigned long long) * (size_t)(tiles + 2), s) != cudaSuccess)
+    return NLB200_ERR_CUDA;
+  const unsigned g = (unsigned)((n + 255) / 256);
+  if (n > 0) {
+    if (dtype == NLB200_F64)
+      slab_flag_kernel<double><<<g, 256, 0, s>>>((const double*)q_dev, n, stride, axis, lo, hi, flags);
+    else
+      slab_flag_kernel<float><<<g, 256, 0, s>>>((const float*)q_dev, n, stride, axis, lo, hi, flags);
+  }
+  scan_kernel<int64_t><<<(unsigned)(tiles - 1 > 0 ? tiles - 1 : 1), SCAN_THREADS, 0, s>>>(flags, n, pos, nullptr, state,
+                                                                                         nullptr, nullptr, 0);
+  if (dtype == NLB200_F64)
+    slab_pack_kernel<double><<<g > 0 ? g : 1, 256, 0, s>>>((const double*)q_dev, gids_dev, gid_base, flags, pos, n,
+                                                          stride, (double*)out_q_dev, out_gid_dev, capacity,
+                                                          out_count_dev);
+  else
+    slab_pack_kernel<float><<<g > 0 ? g : 1, 256, 0, s>>>((const float*)q_dev, gids_dev, gid_base, flags, pos, n, stride,
+                                                         (float*)out_q_dev, out_gid_dev, capacity, out_count_dev);
   return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
 }
 

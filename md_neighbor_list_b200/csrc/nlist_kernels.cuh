@@ -122,12 +122,18 @@ __device__ __forceinline__ bool exact_within(const Vec3<float>& a, const Vec3<fl
 // their true neighbours; a particle more than one cell outside (or NaN) raises FLAG_OUT_OF_BOX because the FP32
 // pre-filter's error bound assumes |x - cell corner| <= 2 cells.
 template <typename T, int STRIDE>
-__global__ void __launch_bounds__(256) bin_kernel(const T* __restrict__ q, int32_t n, GridParams<T> gp,
-                                                  int32_t* __restrict__ cell_count, int2* __restrict__ cell_rank,
-                                                  DeviceStatus* __restrict__ st) {
+__global__ void __launch_bounds__(256) bin_kernel(const T* __restrict__ q, int32_t n, int32_t n_owned,
+                                                  GridParams<T> gp, int32_t* __restrict__ cell_count,
+                                                  int2* __restrict__ cell_rank, DeviceStatus* __restrict__ st) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Vec3<T> p = load_pos<T, STRIDE>(q, i);
+  if (i >= n_owned && p.x != p.x) {
+    // an ABSENT ghost: the fixed-capacity halo buffers of the multi-GPU build are padded with NaN records
+    // (parallel.py); they take part in nothing — no cell, no slot, no row
+    cell_rank[i] = make_int2(-1, 0);
+    return;
+  }
   int32_t cx = static_cast<int32_t>(p.x * gp.ims[0]);
   int32_t cy = static_cast<int32_t>(p.y * gp.ims[1]);
   int32_t cz = static_cast<int32_t>(p.z * gp.ims[2]);
@@ -291,6 +297,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const int2* __restrict__ c
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int2 cr = cell_rank[i];
+  if (cr.x < 0) return;  // absent ghost
   perm[__ldg(cell_start + cr.x) + cr.y] = i;
 }
 
@@ -812,6 +819,7 @@ struct EmitArgs {
   const int32_t* global_ids;  // optional local -> global id map
   int32_t mesh[3];
   int32_t n_total, n_owned;
+  int32_t n_cells;  // cell_start[n_cells] = particles present (n_total minus absent ghosts) = slots in use
   const uint32_t* mask;
   long long n_cap;
   int32_t wi;
@@ -875,7 +883,7 @@ __device__ __forceinline__ void walk_words(const EmitArgs& a, int32_t slot, int3
 // FULL lists: the row length is a popcount of the row's mask words (without its own bit).
 __global__ void __launch_bounds__(128) rowcount_kernel(EmitArgs a) {
   const int32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= a.n_total) return;
+  if (slot >= a.n_total || slot >= __ldg(a.cell_start + a.n_cells)) return;
   const int32_t id = __ldg(a.sorted_ids + slot);
   if (id >= a.n_owned) return;
   int32_t cnt = 0;
@@ -892,7 +900,7 @@ __global__ void __launch_bounds__(128) emit_direct_kernel(EmitArgs a) {
     if (a.offsets[a.n_owned] > a.capacity) return;
   }
   const int32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= a.n_total) return;
+  if (slot >= a.n_total || slot >= __ldg(a.cell_start + a.n_cells)) return;
   const int32_t id = __ldg(a.sorted_ids + slot);
   if (id >= a.n_owned) return;
   const int32_t cell = __ldg(a.slot_cell + slot);
@@ -939,7 +947,7 @@ __global__ void __launch_bounds__(EM_WARPS * 32) emit_kernel(EmitArgs a) {
   const uint32_t line_sa = (uint32_t)__cvta_generic_to_shared(line);
   const int32_t slot = (blockIdx.x * EM_WARPS + warp) * 32 + lane;
   int32_t id = 0x7fffffff;
-  if (slot < a.n_total) id = __ldg(a.sorted_ids + slot);
+  if (slot < a.n_total && slot < __ldg(a.cell_start + a.n_cells)) id = __ldg(a.sorted_ids + slot);
   const bool owned = id < a.n_owned;
   const int32_t cell = owned ? __ldg(a.slot_cell + slot) : 0;
   const int32_t rcmp = (HALF && owned) ? (GID ? __ldg(a.global_ids + id) : id) : 0;
@@ -1224,6 +1232,23 @@ __global__ void __launch_bounds__(256) slab_compact_kernel(const int32_t* __rest
   if (i == 0) *out_count = pos[n];
   if (i >= n) return;
   if (flags[i] && pos[i] < capacity) out[pos[i]] = (int32_t)i;
+}
+
+// halo packing: the selected records (flags/pos from slab_flag_kernel + scan) go to out_q[pos], their global ids to
+// out_gid[pos]; positions >= capacity are dropped (the count tells).  out_q is pre-filled with NaN = absent.
+template <typename T>
+__global__ void __launch_bounds__(256) slab_pack_kernel(const T* __restrict__ q, const int32_t* __restrict__ gids,
+                                                        int32_t gid_base, const int32_t* __restrict__ flags,
+                                                        const int64_t* __restrict__ pos, int64_t n, int stride,
+                                                        T* __restrict__ out_q, int32_t* __restrict__ out_gid,
+                                                        int64_t capacity, int64_t* __restrict__ out_count) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i == 0) *out_count = pos[n];
+  if (i >= n || !flags[i]) return;
+  const int64_t p = pos[i];
+  if (p >= capacity) return;
+  for (int c = 0; c < stride; c++) out_q[p * stride + c] = q[i * stride + c];
+  out_gid[p] = gids != nullptr ? gids[i] : gid_base + (int32_t)i;
 }
 
 template <typename T>

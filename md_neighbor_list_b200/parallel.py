@@ -4,12 +4,16 @@ reference is single-process, single-GPU).
 One process per GPU.  The box is cut into `world` slabs of equal thickness along one axis; rank r owns the particles
 whose coordinate on that axis lies in [lo, hi).  A list row depends only on the particles within the search length of
 its owner, so the only exchange is the ghost layer: before a build every rank sends the owned particles within
-`search_length` of a face to the rank on the other side of that face ({x, y, z, w} records + global ids, one grouped
-send/recv per face over NCCL — NVLink 5 / NVSwitch on a B200 box), then builds rows for its owned particles only:
+`search_length` of a face to the rank on the other side of that face ({x, y, z, w} records + global ids, ONE grouped
+send/recv over NCCL — NVLink 5 / NVSwitch on a B200 box), then builds rows for its owned particles only:
 
-    q_all      = [ owned | ghosts from below | ghosts from above ]
-    global_ids = [ base + arange(n_owned) | received ids ]
+    q_all      = [ owned | ghost slots from below | ghost slots from above ]      (fixed capacity per face)
+    global_ids = [ own ids | received ids ]
     nlb200_build_subset(handle, q_all, n_total, n_owned, global_ids)      (include/nlist_b200.h)
+
+The ghost buffers have a FIXED capacity per face and unused slots hold NaN records, which the build treats as absent
+(include/nlist_b200.h, nlb200_pack_slab): no rank has to learn a count before it posts its receive or launches its
+build, so an exchange + build is enqueued without a single host synchronisation and replays the library's CUDA graph.
 
 Every rank bins on the GLOBAL cell grid (the handle is created with the global box), so the rows it emits are exactly
 the rows a single-GPU build of the whole system would emit for those particles — same partners, same order.  HALF
@@ -17,10 +21,10 @@ lists: the row of the smaller global id keeps the pair, so each pair is emitted 
 particle (ghosts are needed from both faces).  Open boundary (the reference measures distances without minimum image,
 neighlist_cpu.hpp:219-223): the end slabs have one neighbour.
 
-Device path: selection and gather run in the library's CUDA kernels (nlb200_select_slab / nlb200_gather_records).
-The same partition / exchange / ownership logic also accepts CPU tensors (torch ops + the `gloo` backend); that
-branch exists so that the world_size-2 tests can exercise the logic without GPUs — it is not a compute fallback: the
-list build itself is injected by the caller (`build_fn`) and is the CUDA library in the product.
+Device path: selection, packing and padding run in the library's CUDA kernels (nlb200_pack_slab).  The same
+partition / exchange / ownership logic also accepts CPU tensors (torch ops + the `gloo` backend); that branch exists so
+that the world_size-2 tests can exercise the logic without GPUs — it is not a compute fallback: the list build itself
+is injected by the caller (`build_fn`) and is the CUDA library in the product.
 """
 from __future__ import annotations
 
@@ -33,7 +37,7 @@ from . import _lib
 
 class SlabDecomposition:
     def __init__(self, world: int, rank: int, box, search_length: float, axis: int = 2, stride: int = 4,
-                 group=None):
+                 group=None, slack: float = 1.5):
         if not (0 <= rank < world):
             raise ValueError("rank outside [0, world)")
         self.world, self.rank, self.axis, self.stride = int(world), int(rank), int(axis), int(stride)
@@ -47,10 +51,12 @@ class SlabDecomposition:
         if rank == 0:
             self.lo = -float("inf")
         self.group = group
-        self._buf = None  # device workspaces, allocated on first build
-        self._qall = self._gall = None
+        self.slack = float(slack)  # ghost capacity per face = expected count * slack + 1024
+        self._cap = None
+        self._ws = None  # device workspace of nlb200_pack_slab
+        self._qall = self._gall = self._sq = self._sg = self._cnt = self._cnt_host = None
         self._last = None
-        self.last_counts = (0, 0, 0, 0)  # sent below, sent above, received from below, received from above
+        self._gid_default = None
 
     # -- partitioning ---------------------------------------------------------------------------------------------
     def owns(self, q: np.ndarray) -> np.ndarray:
@@ -72,101 +78,108 @@ class SlabDecomposition:
         q[:, self.axis] += self.rank * self.thickness
         return q
 
-    def max_ghosts(self, n_owned: int) -> int:
+    def n_faces(self) -> int:
+        return (1 if self.rank > 0 else 0) + (1 if self.rank + 1 < self.world else 0)
+
+    def ghost_capacity(self, n_owned: int) -> int:
+        """Records moved per face.  Fixed, so that an exchange needs no host synchronisation (nobody has to learn a
+        count before posting a receive or launching the build): unused slots travel as NaN records, which
+        nlb200_build_subset treats as absent."""
         if self.world == 1:
             return 0
-        frac = min(1.0, self.sl / self.thickness)
-        return int(2 * n_owned * frac * 1.5) + 4096
+        if self._cap is None:
+            # both sides of a face must move the same number of records: agree on the largest estimate once
+            # (a collective — every rank makes its first ghost_capacity / max_ghosts / exchange call together)
+            frac = min(1.0, self.sl / self.thickness)
+            cap = (int(n_owned * frac * self.slack) + 1024 + 31) // 32 * 32
+            dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+            t = torch.tensor([cap], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            self._cap = int(t.item())
+        return self._cap
+
+    def max_ghosts(self, n_owned: int) -> int:
+        """Ghost slots behind the owned records: initialise the handle for n_owned + max_ghosts(n_owned)."""
+        return self.n_faces() * self.ghost_capacity(n_owned)
 
     # -- exchange -------------------------------------------------------------------------------------------------
-    def _select(self, q: torch.Tensor, lo: float, hi: float) -> torch.Tensor:
-        """Indices (ascending) of the rows of q with lo <= q[:, axis] < hi."""
-        n = q.shape[0]
-        if not q.is_cuda:
+    def _pack(self, q: torch.Tensor, gid: torch.Tensor, lo: float, hi: float, out_q: torch.Tensor,
+              out_g: torch.Tensor, count: torch.Tensor) -> None:
+        """out_q/out_g[0:k] = the records / global ids with lo <= q[:, axis] < hi (ascending), NaN records behind;
+        count[0] = k (may exceed the capacity: overflow, reported by check())."""
+        n, cap = q.shape[0], out_q.shape[0]
+        if not q.is_cuda:  # logic tests on CPU tensors (gloo); same contract as the CUDA kernels
             z = q[:, self.axis]
-            return torch.nonzero((z >= lo) & (z < hi)).flatten().to(torch.int32)
+            idx = torch.nonzero((z >= lo) & (z < hi)).flatten()
+            count[0] = idx.numel()
+            idx = idx[:cap]
+            out_q.fill_(float("nan"))
+            out_q[:idx.numel()] = q[idx]
+            out_g[:idx.numel()] = gid[idx]
+            return
         L = _lib.lib()
         ws_bytes = L.nlb200_select_slab_workspace(n)
-        b = self._buf
-        if b is None or b["ws"].numel() < ws_bytes or b["idx"].numel() < n:
-            self._buf = b = {"ws": torch.empty(ws_bytes, dtype=torch.uint8, device=q.device),
-                             "idx": torch.empty(max(n, 1), dtype=torch.int32, device=q.device),
-                             "cnt": torch.zeros(1, dtype=torch.int64, device=q.device)}
+        if self._ws is None or self._ws.numel() < ws_bytes:
+            self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
         dtype = _lib.F64 if q.dtype == torch.float64 else _lib.F32
-        s = torch.cuda.current_stream().cuda_stream
-        st = L.nlb200_select_slab(q.data_ptr(), n, dtype, self.stride, self.axis, lo, hi, b["idx"].data_ptr(), n,
-                                  b["cnt"].data_ptr(), b["ws"].data_ptr(), ws_bytes, s)
+        st = L.nlb200_pack_slab(q.data_ptr(), gid.data_ptr(), 0, n, dtype, self.stride, self.axis, lo, hi,
+                                out_q.data_ptr(), out_g.data_ptr(), cap, count.data_ptr(), self._ws.data_ptr(),
+                                ws_bytes, torch.cuda.current_stream().cuda_stream)
         if st != _lib.OK:
-            raise _lib.NlistError(st, "nlb200_select_slab failed")
-        cnt = int(b["cnt"].item())  # host needs the count to size the send (one small D2H per face)
-        return b["idx"][:cnt].clone()
-
-    def _gather(self, q: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
-        if not q.is_cuda:
-            return q[idx.long()].contiguous()
-        out = torch.empty((idx.numel(), self.stride), dtype=q.dtype, device=q.device)
-        if idx.numel():
-            dtype = _lib.F64 if q.dtype == torch.float64 else _lib.F32
-            st = _lib.lib().nlb200_gather_records(q.data_ptr(), idx.data_ptr(), idx.numel(), dtype, self.stride,
-                                                  out.data_ptr(), torch.cuda.current_stream().cuda_stream)
-            if st != _lib.OK:
-                raise _lib.NlistError(st, "nlb200_gather_records failed")
-        return out
+            raise _lib.NlistError(st, "nlb200_pack_slab failed")
 
     def exchange(self, q_owned: torch.Tensor, gid_owned: torch.Tensor):
-        """Returns (q_all, gid_all, n_owned): owned records followed by the ghosts from below and from above."""
+        """Returns (q_all, gid_all, n_owned): the owned records followed by `ghost_capacity` slots per neighbour face
+        (below first), absent slots holding NaN.  One grouped send/recv, no host synchronisation."""
         n = q_owned.shape[0]
         if self.world == 1:
             return q_owned, gid_owned, n
         dev = q_owned.device
-        below, above = self.rank - 1, self.rank + 1
-        send = {}
-        if below >= 0:
-            idx = self._select(q_owned, -float("inf"), self.lo + self.sl)
-            send[below] = (self._gather(q_owned, idx), gid_owned[idx.long()].contiguous())
-        if above < self.world:
-            idx = self._select(q_owned, self.hi - self.sl, float("inf"))
-            send[above] = (self._gather(q_owned, idx), gid_owned[idx.long()].contiguous())
-        # 1. counts (one int64 per face), 2. records + ids — each a single grouped send/recv
-        cnt_out = {p: torch.tensor([send[p][0].shape[0]], dtype=torch.int64, device=dev) for p in send}
-        cnt_in = {p: torch.zeros(1, dtype=torch.int64, device=dev) for p in send}
-        ops = []
-        for p in sorted(send):
-            ops.append(dist.P2POp(dist.isend, cnt_out[p], p, group=self.group))
-            ops.append(dist.P2POp(dist.irecv, cnt_in[p], p, group=self.group))
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
-        # persistent assembly buffers (stable device pointers: identical builds replay the library's CUDA graph);
-        # ghosts are received straight into their final place behind the owned records
-        n_in = {p: int(cnt_in[p].item()) for p in send}
-        n_total = n + sum(n_in.values())
-        if (self._qall is None or self._qall.shape[0] < n_total or self._qall.device != dev
+        cap = self.ghost_capacity(n)
+        peers = [p for p in (self.rank - 1, self.rank + 1) if 0 <= p < self.world]
+        n_total = n + cap * len(peers)
+        if (self._qall is None or self._qall.shape[0] != n_total or self._qall.device != dev
                 or self._qall.dtype != q_owned.dtype):
-            cap = max(n_total, n + self.max_ghosts(n))
-            self._qall = torch.empty((cap, self.stride), dtype=q_owned.dtype, device=dev)
-            self._gall = torch.empty(cap, dtype=torch.int32, device=dev)
+            # persistent buffers: stable device pointers and sizes, so identical builds replay the library's CUDA graph
+            self._qall = torch.empty((n_total, self.stride), dtype=q_owned.dtype, device=dev)
+            self._gall = torch.zeros(n_total, dtype=torch.int32, device=dev)
+            self._sq = {p: torch.empty((cap, self.stride), dtype=q_owned.dtype, device=dev) for p in peers}
+            self._sg = {p: torch.zeros(cap, dtype=torch.int32, device=dev) for p in peers}
+            self._cnt = {p: torch.zeros(1, dtype=torch.int64, device=dev) for p in peers}
+            self._cnt_host = {p: (torch.zeros(1, dtype=torch.int64).pin_memory() if dev.type == "cuda"
+                                  else torch.zeros(1, dtype=torch.int64)) for p in peers}
         self._qall[:n].copy_(q_owned)
         self._gall[:n].copy_(gid_owned)
-        recv, at = {}, n
-        for p in (below, above):
-            if p in send:
-                recv[p] = (self._qall[at:at + n_in[p]], self._gall[at:at + n_in[p]])
-                at += n_in[p]
-        ops = []
-        for p in sorted(send):
-            for k in (0, 1):
-                if send[p][k].numel():
-                    ops.append(dist.P2POp(dist.isend, send[p][k], p, group=self.group))
-                if recv[p][k].numel():
-                    ops.append(dist.P2POp(dist.irecv, recv[p][k], p, group=self.group))
-        if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
-        self.last_counts = (send[below][0].shape[0] if below in send else 0,
-                            send[above][0].shape[0] if above in send else 0,
-                            n_in.get(below, 0), n_in.get(above, 0))
-        self._last = (self._qall[:n_total], self._gall[:n_total], n)
+        for p in peers:
+            if p < self.rank:
+                self._pack(q_owned, gid_owned, -float("inf"), self.lo + self.sl, self._sq[p], self._sg[p], self._cnt[p])
+            else:
+                self._pack(q_owned, gid_owned, self.hi - self.sl, float("inf"), self._sq[p], self._sg[p], self._cnt[p])
+        ops, at = [], n
+        for p in peers:
+            ops.append(dist.P2POp(dist.isend, self._sq[p], p, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, self._qall[at:at + cap], p, group=self.group))
+            ops.append(dist.P2POp(dist.isend, self._sg[p], p, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, self._gall[at:at + cap], p, group=self.group))
+            at += cap
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        for p in peers:
+            self._cnt_host[p].copy_(self._cnt[p], non_blocking=True)
+        self._last = (self._qall, self._gall, n)
         return self._last
+
+    def check(self) -> tuple:
+        """After the build's stream has been synchronised: raises if a face had more ghosts than the capacity;
+        returns the ghosts sent (below, above)."""
+        sent = []
+        for p in (self.rank - 1, self.rank + 1):
+            c = int(self._cnt_host[p][0]) if (self._cnt_host is not None and p in self._cnt_host) else 0
+            if c > (self._cap or 0):
+                raise _lib.NlistError(_lib.ERR_CAPACITY,
+                                      f"{c} ghosts for rank {p} exceed the face capacity {self._cap}: raise `slack`")
+            sent.append(c)
+        return tuple(sent)
 
     def last_assembled(self):
         """(q_all, gid_all, n_owned) of the last exchange — lets one rank rebuild (e.g. under a profiler) without a new
@@ -176,11 +189,14 @@ class SlabDecomposition:
     # -- build ----------------------------------------------------------------------------------------------------
     def global_ids(self, n_owned: int, device) -> torch.Tensor:
         """Global ids of equally sized slabs (local_fcc_slab): rank * n + local index."""
-        return torch.arange(n_owned, dtype=torch.int32, device=device) + self.rank * n_owned
+        if self._gid_default is None or self._gid_default.numel() != n_owned or self._gid_default.device != device:
+            self._gid_default = torch.arange(n_owned, dtype=torch.int32, device=device) + self.rank * n_owned
+        return self._gid_default
 
     def build(self, nl, q_owned: torch.Tensor, stream=None, gid_owned: torch.Tensor | None = None, build_fn=None):
         """Ghost exchange followed by the list build of the owned rows.  `nl` is a VerletListB200 created with the
-        GLOBAL box; `build_fn(q_all, n_owned, gid_all)` replaces nl.build in the CPU logic tests."""
+        GLOBAL box and initialised for n_owned + max_ghosts(n_owned) particles; `build_fn(q_all, n_owned, gid_all)`
+        replaces nl.build in the CPU logic tests."""
         ctx = torch.cuda.stream(stream) if (stream is not None and q_owned.is_cuda) else _null()
         with ctx:
             if gid_owned is None:

@@ -55,6 +55,11 @@ def _worker(rank: int, world: int, port: int):
         def build_fn(q_all, n_owned, gid_all):
             qa = q_all.numpy()
             ga = gid_all.numpy()
+            # fixed-capacity ghost slots: NaN records are absent (the library bins them nowhere); drop them here
+            assert qa.shape[0] == n_owned + dec.max_ghosts(n_owned)
+            present = ~np.isnan(qa[:, 0])
+            assert present[:n_owned].all()
+            qa, ga = qa[present], ga[present]
             # ghosts must be exactly the foreign particles within SL of this slab's faces
             lo, hi = rank * dec.thickness, (rank + 1) * dec.thickness
             z = q[:, 2]
@@ -79,6 +84,8 @@ def _worker(rank: int, world: int, port: int):
         tot = torch.tensor([half_local], dtype=torch.int64)
         dist.all_reduce(tot)
         assert int(tot) == O.build_half(q, SL, box).number_of_pairs
+        sent = dec.check()  # no face overflowed its capacity
+        assert len(sent) == 2 and sum(sent) > 0 and all(c <= dec.ghost_capacity(q_own.shape[0]) for c in sent)
         # every particle is owned by exactly one rank
         cnt = torch.tensor([q_own.shape[0]], dtype=torch.int64)
         dist.all_reduce(cnt)
@@ -98,6 +105,31 @@ def test_slab_thinner_than_search_length_is_rejected():
     from md_neighbor_list_b200.parallel import SlabDecomposition
     with pytest.raises(ValueError):
         SlabDecomposition(4, 0, (50.0, 50.0, 10.0), SL)
+
+
+def _overflow_worker(rank: int, world: int, port: int):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from md_neighbor_list_b200 import NlistError, _lib
+        from md_neighbor_list_b200.parallel import SlabDecomposition
+        q, box = _global_system(world)
+        dec = SlabDecomposition(world, rank, box, SL, axis=2, slack=0.0)
+        dec._cap = 32  # far too small
+        q_own, gid_own = dec.partition(q)
+        dec.build(None, torch.from_numpy(q_own), gid_owned=torch.from_numpy(gid_own), build_fn=lambda *a: None)
+        try:
+            dec.check()
+            raise AssertionError("overflow not detected")
+        except NlistError as e:
+            assert e.status == _lib.ERR_CAPACITY
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ghost_capacity_overflow_is_detected():
+    mp.spawn(_overflow_worker, args=(2, _free_port()), nprocs=2, join=True)
 
 
 def test_single_rank_is_a_no_op():

@@ -386,6 +386,60 @@ def test_owned_subset_with_global_ids(cuda, oracle):
         assert np.array_equal(cnt, ref.number_of_partners[perm[:n_owned]])
 
 
+def test_absent_ghost_slots_and_halo_packing(cuda, oracle):
+    """Fixed-capacity halo buffers (parallel.py): nlb200_pack_slab selects a face's records in ascending order, pads
+    the rest with NaN; NaN ghost records are absent for the build — same rows as without them."""
+    import ctypes as C
+    from md_neighbor_list_b200 import VerletListB200, _lib, workloads
+    torch = cuda
+    L = 24.0
+    q = workloads.fcc(1.0, L)
+    n = q.shape[0]
+    Lb = _lib.lib()
+    qd = torch.from_numpy(q).cuda()
+    cap = 4096
+    out_q = torch.zeros((cap, 4), dtype=torch.float64, device="cuda")
+    out_g = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ws = torch.empty(Lb.nlb200_select_slab_workspace(n), dtype=torch.uint8, device="cuda")
+    gids = (torch.arange(n, dtype=torch.int32, device="cuda") * 3 + 7)
+    st = Lb.nlb200_pack_slab(qd.data_ptr(), gids.data_ptr(), 0, n, _lib.F64, 4, 2, 20.7, float("inf"),
+                             out_q.data_ptr(), out_g.data_ptr(), cap, cnt.data_ptr(), ws.data_ptr(), ws.numel(),
+                             torch.cuda.current_stream().cuda_stream)
+    assert st == _lib.OK
+    sel = np.nonzero(q[:, 2] >= 20.7)[0]
+    k = int(cnt.item())
+    assert k == len(sel) and 0 < k < cap
+    assert np.array_equal(out_q[:k].cpu().numpy(), q[sel])
+    assert np.array_equal(out_g[:k].cpu().numpy(), (sel * 3 + 7).astype(np.int32))
+    assert np.isnan(out_q[k:].cpu().numpy()).all()
+    # a build whose ghost region is [real ghosts | NaN padding] == the build with exactly the real ghosts
+    own = np.nonzero(q[:, 2] < 12.0)[0]
+    gh = np.nonzero((q[:, 2] >= 12.0) & (q[:, 2] < 12.0 + 3.3))[0]
+    pad = 500
+    q_all = np.full((len(own) + len(gh) + pad, 4), np.nan)
+    q_all[:len(own)] = q[own]
+    q_all[len(own):len(own) + len(gh)] = q[gh]
+    g_all = np.zeros(len(q_all), dtype=np.int32)
+    g_all[:len(own)] = own
+    g_all[len(own):len(own) + len(gh)] = gh
+    ref = oracle.build_full(q, 3.3, (L, L, L)).sorted_rows()
+    for mode in ("full_csr", "half_csr"):
+        nl = VerletListB200(3.3, L, L, L, mode=mode)
+        nl.initialize(len(q_all))
+        nl.build(torch.from_numpy(q_all).cuda(), n_owned=len(own), global_ids=torch.from_numpy(g_all).cuda())
+        nl.build(torch.from_numpy(q_all).cuda(), n_owned=len(own), global_ids=torch.from_numpy(g_all).cuda())
+        nl.synchronize()
+        off = nl.offsets().cpu().numpy()
+        lst = sort_rows(oracle, nl.partners().cpu().numpy(), off)
+        for li in range(0, len(own), 11):
+            g = own[li]
+            want = ref.partners[ref.offsets[g]:ref.offsets[g + 1]]
+            if mode == "half_csr":
+                want = want[want > g]
+            assert np.array_equal(lst[off[li]:off[li + 1]], want)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # full-size properties (BASELINE.json configs[2]: 16M uniform, density 1.0, SL 3.3)
 # ---------------------------------------------------------------------------------------------------------------
