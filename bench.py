@@ -177,6 +177,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     L = L_DEFAULT
@@ -199,19 +200,50 @@ def run_ours(args):
         flush.fill_(1)
 
     q_pinned = torch.from_numpy(q).pin_memory()
-    q_dev = q_pinned.to(dev, non_blocking=False)
+    gid_dev = None
+    if halo is None:
+        q_dev = q_pinned.to(dev, non_blocking=False)
+    else:
+        # particles live in the head of the halo assembly buffer: no device-to-device copy per exchange
+        q_dev, gid_dev = halo.owned_view(n_owned, torch.float64, dev)
+        q_dev.copy_(q_pinned)
+        gid_dev.copy_(torch.arange(n_owned, dtype=torch.int32, device=dev) + rank * n_owned)
 
     nl = VerletListB200(SL, *box, dtype="f64", mode="full_csr")
     cap_particles = n_owned if halo is None else n_owned + halo.max_ghosts(n_owned)
-    nl.initialize(cap_particles)
+    # the library estimates the list size from particles / box volume; a rank of a slab decomposition holds 1/world of
+    # the global box, so it is told: density 1.0 * (4/3) pi SL^3 entries per owned row, +30 %
+    max_entries = 0 if halo is None else int(n_owned * 4.18879 * SL ** 3 * 1.3)
+    nl.initialize(cap_particles, max_entries)
 
     def one_build(qd_local=None):
         if halo is None:
             nl.build(q_dev, stream=stream)
         else:
-            halo.build(nl, q_dev, stream)
+            halo.build(nl, q_dev, stream, gid_owned=gid_dev)
+
+    def sync_growing():
+        """synchronize; a capacity the estimate missed (list entries, particles per cell) is grown and the build
+        repeated — outside the timed region"""
+        from md_neighbor_list_b200 import NlistError, _lib
+        for _ in range(4):
+            try:
+                return nl.synchronize()
+            except NlistError as e:
+                if e.status == _lib.ERR_CAPACITY:
+                    nl.reserve(nl.stats().required_entries)
+                elif e.status == _lib.ERR_CELL_CAPACITY:
+                    nl.reserve_cell_capacity(nl.stats().max_in_cell)
+                else:
+                    raise
+                with torch.cuda.stream(stream):
+                    one_build()
+        raise RuntimeError("capacity retries exhausted")
 
     # ---- warm-up ----
+    with torch.cuda.stream(stream):
+        one_build()
+    sync_growing()
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
             one_build()
@@ -260,7 +292,7 @@ def run_ours(args):
     h_cnt = torch.empty(n_owned, dtype=torch.int32).pin_memory()
     h_off = torch.empty(n_owned + 1, dtype=torch.int64).pin_memory()
     h_lst = torch.empty(n_entries, dtype=torch.int32).pin_memory()
-    q_dev2 = torch.empty_like(q_dev)
+    q_dev2 = torch.empty_like(q_dev) if halo is None else q_dev  # multi-GPU: H2D straight into the assembly buffer
     # borrowed views of the library's output buffers (stable until reserve/destroy)
     v_cnt, v_off, v_lst = nl.number_of_partners(), nl.offsets(), nl.partners()
 
@@ -269,7 +301,7 @@ def run_ours(args):
         if halo is None:
             nl.build(q_dev2, stream=stream)
         else:
-            halo.build(nl, q_dev2, stream)
+            halo.build(nl, q_dev2, stream, gid_owned=gid_dev)
         h_cnt.copy_(v_cnt, non_blocking=True)
         h_off.copy_(v_off, non_blocking=True)
         h_lst.copy_(v_lst, non_blocking=True)
@@ -296,7 +328,7 @@ def run_ours(args):
     stage_ms = {}
     if rank == 0:
         nlp = VerletListB200(SL, *box, dtype="f64", mode="full_csr", profile=True)
-        nlp.initialize(cap_particles)
+        nlp.initialize(cap_particles, max_entries)
         reps = 10
         for r in range(reps + 2):
             with torch.cuda.stream(stream):

@@ -212,6 +212,14 @@ int nlb200_pack_slab(const void* q_dev, const int32_t* gids_dev, int32_t gid_bas
                      int axis, double lo, double hi, void* out_q_dev, int32_t* out_gid_dev, int64_t capacity,
                      int64_t* out_count_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
 
+/* Both faces of a slab in one pass: records with q[i][axis] < cut_lo go to the *_lo buffers, records with
+ * q[i][axis] >= cut_hi to the *_hi buffers (either pair may be NULL: end slab), each as in nlb200_pack_slab;
+ * out_counts_dev[0..1] receive the two true counts.  Workspace: 2 x nlb200_select_slab_workspace(n). */
+int nlb200_pack_slab2(const void* q_dev, const int32_t* gids_dev, int64_t n, int dtype, int stride, int axis,
+                      double cut_lo, double cut_hi, void* out_q_lo_dev, int32_t* out_gid_lo_dev, void* out_q_hi_dev,
+                      int32_t* out_gid_hi_dev, int64_t capacity, int64_t* out_counts_dev, void* workspace_dev,
+                      int64_t workspace_bytes, void* stream);
+
 /* Bytes of workspace nlb200_select_slab / nlb200_pack_slab need for n particles. */
 int64_t nlb200_select_slab_workspace(int64_t n);
 

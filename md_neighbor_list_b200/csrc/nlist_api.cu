@@ -48,6 +48,7 @@ struct nlb200_context {
   int32_t* perm = nullptr;
   int32_t* sorted_ids = nullptr;
   int32_t* slot_cell = nullptr;
+  int32_t* slot_gid = nullptr;  // global id per slot (only written when a local -> global map is given)
   float4* rec = nullptr;
   uint32_t* mask = nullptr;  // [27][mask_wi][mask_ncap] pair-mask words
   int32_t mask_wi = 0;       // words per (row, stencil cell): cells may hold up to 32*mask_wi particles
@@ -155,6 +156,7 @@ void free_buffers(nlb200_context* h) {
   F(h->perm);
   F(h->sorted_ids);
   F(h->slot_cell);
+  F(h->slot_gid);
   F(h->mask);
   F(h->rec);
   F(h->counts);
@@ -328,7 +330,7 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     CK(h, stage(ST_CELLSORT));
     const int64_t threads = (int64_t)M * 32;
     cellsort_kernel<T, STRIDE><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(
-        q, gp, h->cell_start, h->perm, h->sorted_ids, h->rec, h->slot_cell);
+        q, gp, h->cell_start, h->perm, h->sorted_ids, h->rec, h->slot_cell, gids, h->slot_gid);
     CK(h, cudaGetLastError());
   }
   const bool half = h->mode == NLB200_HALF_CSR;
@@ -379,7 +381,6 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     pm.rec = h->rec;
     pm.sorted_ids = h->sorted_ids;
     pm.n_owned = (int32_t)n_owned;
-    pm.has_ghosts = n_owned < n_total ? 1 : 0;
     pm.queue = h->queue;
     pm.mask = h->mask;
     pm.n_cap = h->mask_ncap;
@@ -391,6 +392,7 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     em.sorted_ids = h->sorted_ids;
     em.slot_cell = h->slot_cell;
     em.global_ids = gids;
+    em.slot_pid = gids != nullptr ? h->slot_gid : h->sorted_ids;
     for (int d = 0; d < 3; d++) em.mesh[d] = gp.mesh[d];
     em.n_total = n;
     em.n_owned = (int32_t)n_owned;
@@ -418,6 +420,11 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
       if (parts > 8) parts = 8;
       if (h->variant >= 100 && h->variant < 200) parts = h->variant - 100;  // tuning override
       pm.parts = (int32_t)parts;
+      // items per draw from the queue: ~64 draws per resident warp
+      int64_t grab = (M * parts) / (resident * 64);
+      if (grab < 1) grab = 1;
+      if (grab > 64) grab = 64;
+      pm.grab = (int32_t)grab;
       const int64_t need = (M * parts + PM_THREADS / 32 - 1) / (PM_THREADS / 32);
       if (grid > need) grid = need;
       pairmask_kernel<T, STRIDE><<<(unsigned)grid, PM_THREADS, pm_smem, s>>>(pm);
@@ -495,9 +502,12 @@ int alloc_mask(nlb200_context* h, int64_t max_in_cell) {
 
 int64_t estimate_max_in_cell(const nlb200_context* h, int64_t n) {
   // mean occupancy + 6 sigma of a Poisson cell count + slack; lattices stay well below (13-63 at
-  // mean 35.3).  Clustered inputs report NLB200_ERR_CELL_CAPACITY and the caller (or nlb200_build_host) grows it.
+  // mean 35.3).  Floor of 80 (3 words): a rank of a slab decomposition bins on the GLOBAL grid, so n / cells
+  // underestimates its density by the number of ranks.  Clustered inputs report NLB200_ERR_CELL_CAPACITY and the
+  // caller (or nlb200_build_host) grows it.
   const double avg = (double)n / (double)h->n_cells;
-  return (int64_t)(avg + 6.0 * std::sqrt(avg) + 8.0);
+  const int64_t est = (int64_t)(avg + 6.0 * std::sqrt(avg) + 8.0);
+  return est < 80 ? 80 : est;
 }
 
 int alloc_partners(nlb200_context* h, int64_t entries) {
@@ -626,6 +636,7 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
   CK(h, cudaMalloc(&h->perm, sizeof(int32_t) * (size_t)n));
   CK(h, cudaMalloc(&h->sorted_ids, sizeof(int32_t) * (size_t)n));
   CK(h, cudaMalloc(&h->slot_cell, sizeof(int32_t) * (size_t)n));
+  CK(h, cudaMalloc(&h->slot_gid, sizeof(int32_t) * (size_t)n));
   CK(h, cudaMalloc(&h->rec, sizeof(float4) * (size_t)n));
   CK(h, cudaMalloc(&h->counts, sizeof(int32_t) * (size_t)(n + 8)));
   CK(h, cudaMalloc(&h->offsets, sizeof(int64_t) * (size_t)(n + 1)));
@@ -963,6 +974,54 @@ int nlb200_pack_slab(const void* q_dev, const int32_t* gids_dev, int32_t gid_bas
   else
     slab_pack_kernel<float><<<g > 0 ? g : 1, 256, 0, s>>>((const float*)q_dev, gids_dev, gid_base, flags, pos, n, stride,
                                                          (float*)out_q_dev, out_gid_dev, capacity, out_count_dev);
+  return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
+}
+
+int nlb200_pack_slab2(const void* q_dev, const int32_t* gids_dev, int64_t n, int dtype, int stride, int axis,
+                      double cut_lo, double cut_hi, void* out_q_lo_dev, int32_t* out_gid_lo_dev, void* out_q_hi_dev,
+                      int32_t* out_gid_hi_dev, int64_t capacity, int64_t* out_counts_dev, void* workspace_dev,
+                      int64_t workspace_bytes, void* stream) {
+  if (n < 0 || capacity < 0 || axis < 0 || axis > 2 || (stride != 3 && stride != 4)) return NLB200_ERR_INVALID;
+  const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE + 1;
+  const size_t o_pos = align_up(sizeof(int32_t) * (size_t)(n + 8), 256);
+  const size_t o_state = align_up(o_pos + sizeof(int64_t) * (size_t)(n + 1), 256);
+  const size_t half = align_up(o_state + sizeof(unsigned long long) * (size_t)(tiles + 2), 256);
+  if (workspace_dev == nullptr || (size_t)workspace_bytes < 2 * half) return NLB200_ERR_CAPACITY;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace_dev);
+  int32_t* flags[2] = {reinterpret_cast<int32_t*>(ws), reinterpret_cast<int32_t*>(ws + half)};
+  int64_t* pos[2] = {reinterpret_cast<int64_t*>(ws + o_pos), reinterpret_cast<int64_t*>(ws + half + o_pos)};
+  unsigned long long* state[2] = {reinterpret_cast<unsigned long long*>(ws + o_state),
+                                  reinterpret_cast<unsigned long long*>(ws + half + o_state)};
+  const size_t esz = dtype == NLB200_F64 ? 8 : 4;
+  void* outs[2] = {out_q_lo_dev, out_q_hi_dev};
+  for (int f = 0; f < 2; f++) {
+    // all-ones bytes are a NaN in both precisions: every slot starts as an absent ghost
+    if (outs[f] && capacity > 0 && cudaMemsetAsync(outs[f], 0xFF, (size_t)capacity * stride * esz, s) != cudaSuccess)
+      return NLB200_ERR_CUDA;
+    if (cudaMemsetAsync(state[f], 0, sizeof(unsigned long long) * (size_t)(tiles + 2), s) != cudaSuccess)
+      return NLB200_ERR_CUDA;
+  }
+  const unsigned g = (unsigned)((n + 255) / 256);
+  if (n > 0) {
+    if (dtype == NLB200_F64)
+      slab_flag2_kernel<double><<<g, 256, 0, s>>>((const double*)q_dev, n, stride, axis, cut_lo, cut_hi, flags[0],
+                                                 flags[1]);
+    else
+      slab_flag2_kernel<float><<<g, 256, 0, s>>>((const float*)q_dev, n, stride, axis, cut_lo, cut_hi, flags[0],
+                                                flags[1]);
+  }
+  for (int f = 0; f < 2; f++)
+    scan_kernel<int64_t><<<(unsigned)(tiles - 1 > 0 ? tiles - 1 : 1), SCAN_THREADS, 0, s>>>(
+        flags[f], n, pos[f], nullptr, state[f], nullptr, nullptr, 0);
+  if (dtype == NLB200_F64)
+    slab_pack2_kernel<double><<<g > 0 ? g : 1, 256, 0, s>>>(
+        (const double*)q_dev, gids_dev, flags[0], pos[0], flags[1], pos[1], n, stride, (double*)out_q_lo_dev,
+        out_gid_lo_dev, (double*)out_q_hi_dev, out_gid_hi_dev, capacity, out_counts_dev);
+  else
+    slab_pack2_kernel<float><<<g > 0 ? g : 1, 256, 0, s>>>(
+        (const float*)q_dev, gids_dev, flags[0], pos[0], flags[1], pos[1], n, stride, (float*)out_q_lo_dev,
+        out_gid_lo_dev, (float*)out_q_hi_dev, out_gid_hi_dev, capacity, out_counts_dev);
   return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
 }
 

@@ -312,7 +312,9 @@ __global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, 
                                                        const int32_t* __restrict__ cell_start,
                                                        const int32_t* __restrict__ perm,
                                                        int32_t* __restrict__ sorted_ids, float4* __restrict__ rec,
-                                                       int32_t* __restrict__ slot_cell) {
+                                                       int32_t* __restrict__ slot_cell,
+                                                       const int32_t* __restrict__ global_ids,
+                                                       int32_t* __restrict__ slot_pid) {
   const int32_t cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (cell >= gp.n_cells) return;
   const int lane = lane_id();
@@ -344,6 +346,9 @@ __global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, 
       sorted_ids[beg + rank] = id;
       rec[beg + rank] = r;
       slot_cell[beg + rank] = cell;
+      // the id a row reports for this particle: with a local -> global map (multi-GPU) the emission gathers the
+      // global id straight from the slot instead of slot -> local id -> global id
+      if (global_ids != nullptr) slot_pid[beg + rank] = __ldg(global_ids + id);
     }
   }
 }
@@ -583,7 +588,6 @@ struct PairMaskArgs {
   const float4* rec;
   const int32_t* sorted_ids;
   int32_t n_owned;
-  int32_t has_ghosts;  // n_owned < n_total: rows of ghost particles are skipped
   uint32_t* mask;      // [27][wi][n_cap]
   long long n_cap;
   int32_t wi;
@@ -591,6 +595,7 @@ struct PairMaskArgs {
   int32_t* queue;   // item counter (zeroed per build): warps draw (cell, part) items from it
   int32_t parts;   // items per cell: part p takes the candidate chunks p, p + parts, ...  (small systems: more
                    // items than resident warps, so that the queue can balance them)
+  int32_t grab;    // items drawn per atomic (large systems: the single counter would otherwise serialise the warps)
   DeviceStatus* st;
 };
 
@@ -623,13 +628,14 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
   unsigned long long band_local = 0, cand_local = 0;
 
   const long long n_items = (long long)gp.n_cells * a.parts;
-  int32_t item = 0;
-  if (lane == 0) item = atomicAdd(a.queue, 1);
-  item = __shfl_sync(0xffffffffu, item, 0);
-  while (item < n_items) {
-    const int32_t cell = item / a.parts, part = item - cell * a.parts;
+  int32_t base = 0;
+  if (lane == 0) base = atomicAdd(a.queue, a.grab);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  while (base < n_items) {
     int32_t next = 0;
-    if (lane == 0) next = atomicAdd(a.queue, 1);  // in flight while this cell is processed
+    if (lane == 0) next = atomicAdd(a.queue, a.grab);  // in flight while this batch is processed
+    for (int32_t item = base; item < base + a.grab && item < n_items; item++) {
+    const int32_t cell = item / a.parts, part = item - cell * a.parts;
     const int32_t ibeg = __ldg(a.cell_start + cell);
     int32_t ni = __ldg(a.cell_start + cell + 1) - ibeg;
     if (ni > 0) {
@@ -717,9 +723,8 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
             zj[k] = fmaf(t_tz[r], msz, rj.z);
             wj[k] = -0.5f * fmaf(xj[k], xj[k], fmaf(yj[k], yj[k], zj[k] * zj[k]));
             sj[k] = s;
-            bool store = true;
-            if (a.has_ghosts) store = __ldg(a.sorted_ids + s) < a.n_owned;
-            if (store) oj[k] = (t_o[r] + (col == 0 ? oxs[0] : (col == 1 ? oxs[1] : oxs[2]))) * a.wi;
+            // rec.w carries the particle's local id (cellsort_kernel): rows of ghosts (id >= n_owned) are not stored
+            if (__float_as_int(rj.w) < a.n_owned) oj[k] = (t_o[r] + (col == 0 ? oxs[0] : (col == 1 ? oxs[1] : oxs[2]))) * a.wi;
           }
         }
         f32x2 X[PM_RJ / 2], Y[PM_RJ / 2], Z[PM_RJ / 2], W[PM_RJ / 2];
@@ -806,7 +811,8 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
         }
       }
     }
-    item = __shfl_sync(0xffffffffu, next, 0);
+    }
+    base = __shfl_sync(0xffffffffu, next, 0);
   }
   if (cand_local) atomicAdd(&a.st->candidates, cand_local);
   if (band_local) atomicAdd(&a.st->band_tests, band_local);
@@ -816,7 +822,8 @@ struct EmitArgs {
   const int32_t* cell_start;
   const int32_t* sorted_ids;
   const int32_t* slot_cell;
-  const int32_t* global_ids;  // optional local -> global id map
+  const int32_t* global_ids;  // optional local -> global id map (HALF rule of the row's own particle)
+  const int32_t* slot_pid;    // partner id reported for a slot: sorted_ids, or the global ids in slot order
   int32_t mesh[3];
   int32_t n_total, n_owned;
   int32_t n_cells;  // cell_start[n_cells] = particles present (n_total minus absent ghosts) = slots in use
@@ -908,12 +915,11 @@ __global__ void __launch_bounds__(128) emit_direct_kernel(EmitArgs a) {
   int32_t* wp = COUNT ? nullptr : a.partners + a.offsets[id];
   int32_t cnt = 0;
   walk_words<!HALF>(a, slot, cell, [&](uint32_t word, int32_t first) {
-    const int32_t* ids = a.sorted_ids + first;
+    const int32_t* ids = a.slot_pid + first;
     while (word) {
       const int b = __clz(word);
       word &= ~(0x80000000u >> b);
-      int32_t pid = __ldg(ids + b);
-      if (GID) pid = __ldg(a.global_ids + pid);
+      const int32_t pid = __ldg(ids + b);
       if (HALF && !(pid > mycmp)) continue;
       if (!COUNT) wp[cnt] = pid;
       cnt++;
@@ -965,31 +971,21 @@ __global__ void __launch_bounds__(EM_WARPS * 32) emit_kernel(EmitArgs a) {
       int32_t* out = a.partners + dst + done;
       // head: scalar stores until the row position is 16-byte aligned
       while (k < fill && ((reinterpret_cast<uintptr_t>(out + k) & 15) != 0)) {
-        int32_t pid = __ldg(a.sorted_ids + line[k]);
-        if (GID) pid = __ldg(a.global_ids + pid);
-        out[k] = pid;
+        out[k] = __ldg(a.slot_pid + line[k]);
         k++;
       }
       while (k + 4 <= fill) {
         int4 v;
-        v.x = __ldg(a.sorted_ids + line[k]);
-        v.y = __ldg(a.sorted_ids + line[k + 1]);
-        v.z = __ldg(a.sorted_ids + line[k + 2]);
-        v.w = __ldg(a.sorted_ids + line[k + 3]);
-        if (GID) {
-          v.x = __ldg(a.global_ids + v.x);
-          v.y = __ldg(a.global_ids + v.y);
-          v.z = __ldg(a.global_ids + v.z);
-          v.w = __ldg(a.global_ids + v.w);
-        }
+        v.x = __ldg(a.slot_pid + line[k]);
+        v.y = __ldg(a.slot_pid + line[k + 1]);
+        v.z = __ldg(a.slot_pid + line[k + 2]);
+        v.w = __ldg(a.slot_pid + line[k + 3]);
         *reinterpret_cast<int4*>(out + k) = v;
         k += 4;
       }
       if (final) {
         while (k < fill) {
-          int32_t pid = __ldg(a.sorted_ids + line[k]);
-          if (GID) pid = __ldg(a.global_ids + pid);
-          out[k] = pid;
+          out[k] = __ldg(a.slot_pid + line[k]);
           k++;
         }
       }
@@ -998,8 +994,7 @@ __global__ void __launch_bounds__(EM_WARPS * 32) emit_kernel(EmitArgs a) {
       // HALF: the j > i filter compacts the stream, so the kept ids are stored one by one
       int32_t* out = a.partners + dst;
       for (; k < fill; k++) {
-        int32_t pid = __ldg(a.sorted_ids + line[k]);
-        if (GID) pid = __ldg(a.global_ids + pid);
+        const int32_t pid = __ldg(a.slot_pid + line[k]);
         if (pid > rcmp) {
           if (!COUNT) out[done] = pid;
           done++;
@@ -1232,6 +1227,52 @@ __global__ void __launch_bounds__(256) slab_compact_kernel(const int32_t* __rest
   if (i == 0) *out_count = pos[n];
   if (i >= n) return;
   if (flags[i] && pos[i] < capacity) out[pos[i]] = (int32_t)i;
+}
+
+// both faces of a slab in one pass over the positions: flags_lo[i] = q[i][axis] < cut_lo, flags_hi[i] = q[i][axis] >= cut_hi
+template <typename T>
+__global__ void __launch_bounds__(256) slab_flag2_kernel(const T* __restrict__ q, int64_t n, int stride, int axis,
+                                                         double cut_lo, double cut_hi, int32_t* __restrict__ flags_lo,
+                                                         int32_t* __restrict__ flags_hi) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = (double)q[i * stride + axis];
+  flags_lo[i] = (v < cut_lo) ? 1 : 0;
+  flags_hi[i] = (v >= cut_hi) ? 1 : 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) slab_pack2_kernel(const T* __restrict__ q, const int32_t* __restrict__ gids,
+                                                         const int32_t* __restrict__ flags_lo,
+                                                         const int64_t* __restrict__ pos_lo,
+                                                         const int32_t* __restrict__ flags_hi,
+                                                         const int64_t* __restrict__ pos_hi, int64_t n, int stride,
+                                                         T* __restrict__ out_q_lo, int32_t* __restrict__ out_gid_lo,
+                                                         T* __restrict__ out_q_hi, int32_t* __restrict__ out_gid_hi,
+                                                         int64_t capacity, int64_t* __restrict__ out_counts) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i == 0) {
+    out_counts[0] = pos_lo[n];
+    out_counts[1] = pos_hi[n];
+  }
+  if (i >= n) return;
+  const bool lo = flags_lo[i] != 0 && out_q_lo != nullptr, hi = flags_hi[i] != 0 && out_q_hi != nullptr;
+  if (!lo && !hi) return;
+  const int32_t g = gids != nullptr ? gids[i] : (int32_t)i;
+  if (lo) {
+    const int64_t p = pos_lo[i];
+    if (p < capacity) {
+      for (int c = 0; c < stride; c++) out_q_lo[p * stride + c] = q[i * stride + c];
+      out_gid_lo[p] = g;
+    }
+  }
+  if (hi) {
+    const int64_t p = pos_hi[i];
+    if (p < capacity) {
+      for (int c = 0; c < stride; c++) out_q_hi[p * stride + c] = q[i * stride + c];
+      out_gid_hi[p] = g;
+    }
+  }
 }
 
 // halo packing: the selected records (flags/pos from slab_flag_kernel + scan) go to out_q[pos], their global ids to

@@ -128,6 +128,16 @@ class SlabDecomposition:
         if st != _lib.OK:
             raise _lib.NlistError(st, "nlb200_pack_slab failed")
 
+    def _alloc(self, n_total, cap, peers, dtype, dev):
+        # persistent buffers: stable device pointers and sizes, so identical builds replay the library's CUDA graph
+        self._qall = torch.empty((n_total, self.stride), dtype=dtype, device=dev)
+        self._gall = torch.zeros(n_total, dtype=torch.int32, device=dev)
+        self._sq = {p: torch.empty((cap, self.stride), dtype=dtype, device=dev) for p in peers}
+        self._sg = {p: torch.zeros(cap, dtype=torch.int32, device=dev) for p in peers}
+        self._cnt = {p: torch.zeros(1, dtype=torch.int64, device=dev) for p in peers}
+        self._cnt_host = {p: (torch.zeros(1, dtype=torch.int64).pin_memory() if dev.type == "cuda"
+                              else torch.zeros(1, dtype=torch.int64)) for p in peers}
+
     def exchange(self, q_owned: torch.Tensor, gid_owned: torch.Tensor):
         """Returns (q_all, gid_all, n_owned): the owned records followed by `ghost_capacity` slots per neighbour face
         (below first), absent slots holding NaN.  One grouped send/recv, no host synchronisation."""
@@ -140,21 +150,42 @@ class SlabDecomposition:
         n_total = n + cap * len(peers)
         if (self._qall is None or self._qall.shape[0] != n_total or self._qall.device != dev
                 or self._qall.dtype != q_owned.dtype):
-            # persistent buffers: stable device pointers and sizes, so identical builds replay the library's CUDA graph
-            self._qall = torch.empty((n_total, self.stride), dtype=q_owned.dtype, device=dev)
-            self._gall = torch.zeros(n_total, dtype=torch.int32, device=dev)
-            self._sq = {p: torch.empty((cap, self.stride), dtype=q_owned.dtype, device=dev) for p in peers}
-            self._sg = {p: torch.zeros(cap, dtype=torch.int32, device=dev) for p in peers}
-            self._cnt = {p: torch.zeros(1, dtype=torch.int64, device=dev) for p in peers}
-            self._cnt_host = {p: (torch.zeros(1, dtype=torch.int64).pin_memory() if dev.type == "cuda"
-                                  else torch.zeros(1, dtype=torch.int64)) for p in peers}
-        self._qall[:n].copy_(q_owned)
-        self._gall[:n].copy_(gid_owned)
-        for p in peers:
-            if p < self.rank:
-                self._pack(q_owned, gid_owned, -float("inf"), self.lo + self.sl, self._sq[p], self._sg[p], self._cnt[p])
-            else:
-                self._pack(q_owned, gid_owned, self.hi - self.sl, float("inf"), self._sq[p], self._sg[p], self._cnt[p])
+            self._alloc(n_total, cap, peers, q_owned.dtype, dev)
+        if q_owned.data_ptr() != self._qall.data_ptr():  # owned_view(): the caller already writes in place
+            self._qall[:n].copy_(q_owned)
+        if gid_owned.data_ptr() != self._gall.data_ptr():
+            self._gall[:n].copy_(gid_owned)
+        lo_p, hi_p = self.rank - 1, self.rank + 1
+        if q_owned.is_cuda:
+            # both faces in one pass over the positions (nlb200_pack_slab2)
+            L = _lib.lib()
+            ws_bytes = 2 * L.nlb200_select_slab_workspace(n) + 512
+            if self._ws is None or self._ws.numel() < ws_bytes:
+                self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                self._cnt2 = torch.zeros(2, dtype=torch.int64, device=dev)
+            dtype = _lib.F64 if q_owned.dtype == torch.float64 else _lib.F32
+            has_lo, has_hi = lo_p in self._sq, hi_p in self._sq
+            st = L.nlb200_pack_slab2(
+                q_owned.data_ptr(), gid_owned.data_ptr(), n, dtype, self.stride, self.axis,
+                self.lo + self.sl if has_lo else -float("inf"), self.hi - self.sl if has_hi else float("inf"),
+                self._sq[lo_p].data_ptr() if has_lo else None, self._sg[lo_p].data_ptr() if has_lo else None,
+                self._sq[hi_p].data_ptr() if has_hi else None, self._sg[hi_p].data_ptr() if has_hi else None,
+                cap, self._cnt2.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                torch.cuda.current_stream().cuda_stream)
+            if st != _lib.OK:
+                raise _lib.NlistError(st, "nlb200_pack_slab2 failed")
+            if has_lo:
+                self._cnt[lo_p] = self._cnt2[0:1]
+            if has_hi:
+                self._cnt[hi_p] = self._cnt2[1:2]
+        else:
+            for p in peers:
+                if p < self.rank:
+                    self._pack(q_owned, gid_owned, -float("inf"), self.lo + self.sl, self._sq[p], self._sg[p],
+                               self._cnt[p])
+                else:
+                    self._pack(q_owned, gid_owned, self.hi - self.sl, float("inf"), self._sq[p], self._sg[p],
+                               self._cnt[p])
         ops, at = [], n
         for p in peers:
             ops.append(dist.P2POp(dist.isend, self._sq[p], p, group=self.group))
@@ -168,6 +199,17 @@ class SlabDecomposition:
             self._cnt_host[p].copy_(self._cnt[p], non_blocking=True)
         self._last = (self._qall, self._gall, n)
         return self._last
+
+    def owned_view(self, n_owned: int, dtype=torch.float64, device=None):
+        """(positions, global ids) views of the first n_owned slots of the assembly buffers: a caller that keeps its
+        particles there saves the device-to-device copy of every exchange (the buffers are allocated here)."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        cap = self.ghost_capacity(n_owned)
+        peers = [p for p in (self.rank - 1, self.rank + 1) if 0 <= p < self.world]
+        n_total = n_owned + cap * len(peers)
+        if self._qall is None or self._qall.shape[0] != n_total:
+            self._alloc(n_total, cap, peers, dtype, dev)
+        return self._qall[:n_owned], self._gall[:n_owned]
 
     def check(self) -> tuple:
         """After the build's stream has been synchronised: raises if a face had more ghosts than the capacity;
