@@ -328,8 +328,9 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->cell_rank, n, h->cell_start, h->perm);
     CK(h, cudaGetLastError());
     CK(h, stage(ST_CELLSORT));
-    const int64_t threads = (int64_t)M * 32;
-    cellsort_kernel<T, STRIDE><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(
+    int64_t cs_blocks = ((int64_t)M * 32 + 127) / 128;
+    if (cs_blocks > (int64_t)h->sm_count * 64) cs_blocks = (int64_t)h->sm_count * 64;  // warps stride over the cells
+    cellsort_kernel<T, STRIDE><<<(unsigned)cs_blocks, 128, 0, s>>>(
         q, gp, h->cell_start, h->perm, h->sorted_ids, h->rec, h->slot_cell, gids, h->slot_gid);
     CK(h, cudaGetLastError());
   }

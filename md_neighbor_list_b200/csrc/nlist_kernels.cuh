@@ -315,12 +315,13 @@ __global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, 
                                                        int32_t* __restrict__ slot_cell,
                                                        const int32_t* __restrict__ global_ids,
                                                        int32_t* __restrict__ slot_pid) {
-  const int32_t cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (cell >= gp.n_cells) return;
+  // warps stride over the cells (a slab rank bins on the global grid: most of its cells are empty)
   const int lane = lane_id();
+  const int32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (int32_t cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; cell < gp.n_cells; cell += warps) {
   const int32_t beg = __ldg(cell_start + cell);
   const int32_t cnt = __ldg(cell_start + cell + 1) - beg;
-  if (cnt == 0) return;
+  if (cnt == 0) continue;
   const int32_t cx = cell % gp.mesh[0];
   const int32_t cy = (cell / gp.mesh[0]) % gp.mesh[1];
   const int32_t cz = cell / (gp.mesh[0] * gp.mesh[1]);
@@ -350,6 +351,7 @@ __global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, 
       // global id straight from the slot instead of slot -> local id -> global id
       if (global_ids != nullptr) slot_pid[beg + rank] = __ldg(global_ids + id);
     }
+  }
   }
 }
 
