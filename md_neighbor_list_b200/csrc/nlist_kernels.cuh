@@ -10,21 +10,24 @@
 //         -> cellsort_kernel   ids ascending inside a cell + cell-sorted FP32 position records
 //                                                                (the SortPtclData / CopyGather the reference stubbed
 //                                                                 out: neighlist_cpu.hpp:176-180, neighlist_gpu.hpp:144-151)
-//         -> search_kernel<COUNT>  pair search, counts only      (kernel_impl.cuh:3-436, neighlist_cpu.hpp:239-359)
+//         -> pairmask_kernel   pair search: every ordered pair tested once, verdicts kept as bit masks
+//                                                                (kernel_impl.cuh:3-436, neighlist_cpu.hpp:239-359)
+//         -> rowcount_kernel   FULL: row length = popcount  /  emit_kernel<COUNT>  HALF: ids needed to count
 //         -> scan_kernel       counts -> CSR offsets             (MakeNeighListForEachPtcl, neighlist_cpu.hpp:361-367)
-//         -> search_kernel<FILL>   pair search, emission into CSR (neighlist_cpu.hpp:369-372; replaces the
-//                                                                 row-major buffer + cublasSgeam transpose,
-//                                                                 kernel_impl.cuh:217-239)
+//         -> emit_kernel       bits -> partner ids, rows written with 16-byte stores (neighlist_cpu.hpp:369-372;
+//                                                                 replaces the row-major buffer + cublasSgeam
+//                                                                 transpose, kernel_impl.cuh:217-239)
 //         -> [sort_rows_kernel] [ell_kernel]
+//   search_kernel (one CTA per cell, test evaluated in a count and a fill pass) is the round-0 search, kept as
+//   NLB200_OPT_KERNEL_VARIANT = 1 and for NLB200_OPT_EXACT_ONLY; emit_direct_kernel is an ablation (variant 3).
 //
 // Not a port: the reference searches with one thread/warp per particle gathering unsorted positions by id and writes
-// an ELL matrix.  Here positions are physically cell-sorted as 16-byte FP32 records relative to their cell corner,
-// a CTA stages the <= 9 contiguous x-runs of its stencil into shared memory in CTA-local coordinates, each thread
-// owns one i-particle and tests it against warp-broadcast j records with a 4-instruction FP32 dot-form pre-filter
-//   |xi-xj|^2 <= SL^2  <=>  xi.xj - |xj|^2/2 >= (|xi|^2 - SL^2)/2
-// whose rigorous error band (E) decides definite hit / definite miss; the few candidates inside the
+// an ELL matrix.  Here positions are physically cell-sorted as 16-byte FP32 records relative to their cell corner; the
+// distance test is a dot-form FP32 pre-filter
+//   |xi-xj|^2 <= SL^2  <=>  xi.xj - |xj|^2/2 - (|xi|^2 - SL^2)/2 >= 0          (3 FFMA2 + 1 FADD2 per two tests)
+// whose rigorous error band (E) separates definite hits and misses; the few candidates inside the
 // band are re-tested exactly in the caller's precision with the reference's rounding order, so verdicts are
-// bit-identical to the reference while the hot loop runs on the FP32 pipe.
+// bit-identical to the reference while the hot loop runs on the packed FP32 pipe.
 #pragma once
 
 #include <cuda_runtime.h>
