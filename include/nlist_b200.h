@@ -194,6 +194,21 @@ const char* nlb200_last_error(nlb200_handle h);
 const char* nlb200_status_string(int status);
 int nlb200_version(void);
 
+/* ---- callers either side of the build ------------------------------------------------------------ */
+
+/* f2, Verlet-list lifetime.  The search length includes a margin (make_list.cpp:23: 3.0 + 0.3) so that a list stays
+ * valid while no particle has moved more than margin/2 since it was built; the reference's driver fakes this with 100
+ * identical rebuilds (make_list.cpp:153-155).  nlb200_track_reference remembers the positions a list was built from
+ * (device copy, stream-ordered); nlb200_max_displacement returns max_i |q_now[i] - q_ref[i]| (synchronises `stream`):
+ * rebuild when it exceeds margin/2. */
+int nlb200_track_reference(nlb200_handle h, const void* q_dev, int64_t n, void* stream);
+int nlb200_max_displacement(nlb200_handle h, const void* q_dev, int64_t n, void* stream, double* max_disp_host);
+
+/* f1, the physical reorder the reference stubbed out (SortPtclData, neighlist_cpu.hpp:176-180; CopyGather + SORT_FREQ,
+ * neighlist_gpu.hpp:72,144-151): dst[slot] = src[sorted_ids[slot]] for a per-particle array of `width` elements of
+ * elem_bytes (4 or 8) each, in the cell order of the last build — lets a downstream kernel read coalesced. */
+int nlb200_gather_sorted(nlb200_handle h, const void* src_dev, int elem_bytes, int width, void* dst_dev, void* stream);
+
 /* ---- adjacent utilities (device side of the drivers) ---------------------------------------------------------- */
 
 /* Ghost selection for slab decomposition: writes the indices i < n with lo <= q[i][axis] < hi into

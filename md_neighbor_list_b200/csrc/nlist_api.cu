@@ -4,6 +4,7 @@
 // (94-112), Initialize (268-287), MakeNeighList (289-466), accessors (468-487).  This file is its B200-native
 // counterpart: per-handle state instead of globals/statics, one stream-ordered kernel chain with no host
 // synchronisation inside a build, the chain replayed as a CUDA graph, capacities checked on the device and reported.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -62,6 +63,10 @@ struct nlb200_context {
   int32_t* ell_prev = nullptr;
   int64_t ell_last_n = -1;  // row stride of the ELL view written by the previous build
   void* q_stage = nullptr;  // device staging for nlb200_build_host
+  void* q_ref = nullptr;    // positions remembered by nlb200_track_reference (Verlet-list lifetime)
+  int64_t q_ref_n = 0;
+  unsigned long long* disp_dev = nullptr;
+  unsigned long long* disp_host = nullptr;  // pinned
   cudaStream_t own_stream = nullptr;
 
   // host mirrors
@@ -166,6 +171,10 @@ void free_buffers(nlb200_context* h) {
   F(h->ell);
   F(h->ell_prev);
   F(h->q_stage);
+  F(h->q_ref);
+  F(h->disp_dev);
+  if (h->disp_host) cudaFreeHost(h->disp_host);
+  h->disp_host = nullptr;
   if (h->status_host) cudaFreeHost(h->status_host);
   h->status_host = nullptr;
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -905,6 +914,69 @@ const char* nlb200_stage_name(int stage_id) {
 int64_t nlb200_required_entries(nlb200_handle h) { return (h && h->have_result) ? h->stats.required_entries : -1; }
 
 const char* nlb200_last_error(nlb200_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+// ---- callers either side of the build ------------------------------------------------------------
+
+int nlb200_track_reference(nlb200_handle h, const void* q_dev, int64_t n, void* stream) {
+  if (!h) return NLB200_ERR_INVALID;
+  if (!h->initialized) return fail(h, NLB200_ERR_STATE, "track before initialize");
+  if (n < 0 || n > h->max_n || (n > 0 && !q_dev)) return fail(h, NLB200_ERR_INVALID, "particle count out of range");
+  const size_t esz = h->dtype == NLB200_F64 ? 8 : 4;
+  if (!h->q_ref) {
+    CK(h, cudaMalloc(&h->q_ref, (size_t)(h->max_n > 0 ? h->max_n : 1) * h->stride * esz));
+    CK(h, cudaMalloc(&h->disp_dev, sizeof(unsigned long long)));
+    CK(h, cudaMallocHost(&h->disp_host, sizeof(unsigned long long)));
+  }
+  if (n) CK(h, cudaMemcpyAsync(h->q_ref, q_dev, (size_t)n * h->stride * esz, cudaMemcpyDeviceToDevice,
+                               reinterpret_cast<cudaStream_t>(stream)));
+  h->q_ref_n = n;
+  return NLB200_OK;
+}
+
+int nlb200_max_displacement(nlb200_handle h, const void* q_dev, int64_t n, void* stream, double* max_disp_host) {
+  if (!h || !max_disp_host) return NLB200_ERR_INVALID;
+  if (!h->q_ref) return fail(h, NLB200_ERR_STATE, "nlb200_max_displacement before nlb200_track_reference");
+  if (n != h->q_ref_n) return fail(h, NLB200_ERR_INVALID, "particle count differs from the tracked reference");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  CK(h, cudaMemsetAsync(h->disp_dev, 0, sizeof(unsigned long long), s));
+  if (n > 0) {
+    const unsigned g = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8);
+    if (h->dtype == NLB200_F64)
+      max_disp2_kernel<double><<<g, 256, 0, s>>>((const double*)q_dev, (const double*)h->q_ref, n, h->stride,
+                                                h->disp_dev);
+    else
+      max_disp2_kernel<float><<<g, 256, 0, s>>>((const float*)q_dev, (const float*)h->q_ref, n, h->stride,
+                                               h->disp_dev);
+    CK(h, cudaGetLastError());
+  }
+  CK(h, cudaMemcpyAsync(h->disp_host, h->disp_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CK(h, cudaStreamSynchronize(s));
+  double d2;
+  memcpy(&d2, h->disp_host, sizeof(double));
+  *max_disp_host = std::sqrt(d2);
+  return NLB200_OK;
+}
+
+int nlb200_gather_sorted(nlb200_handle h, const void* src_dev, int elem_bytes, int width, void* dst_dev, void* stream) {
+  if (!h) return NLB200_ERR_INVALID;
+  if (!h->initialized || (!h->build_pending && !h->have_result))
+    return fail(h, NLB200_ERR_STATE, "gather_sorted needs a build (the cell order comes from it)");
+  if ((elem_bytes != 4 && elem_bytes != 8) || width < 1 || width > 16 || !src_dev || !dst_dev)
+    return fail(h, NLB200_ERR_INVALID, "gather_sorted: 4- or 8-byte elements, 1..16 per particle");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t total = h->last_n * width;
+  if (total == 0) return NLB200_OK;
+  const unsigned g = (unsigned)((total + 255) / 256);
+  const int32_t* present = h->cell_start + h->n_cells;
+  if (elem_bytes == 8)
+    gather_sorted_kernel<double><<<g, 256, 0, s>>>((const double*)src_dev, h->sorted_ids, present, width,
+                                                  (double*)dst_dev);
+  else
+    gather_sorted_kernel<float><<<g, 256, 0, s>>>((const float*)src_dev, h->sorted_ids, present, width,
+                                                 (float*)dst_dev);
+  CK(h, cudaGetLastError());
+  return NLB200_OK;
+}
 
 // ---- adjacent utilities ----------------------------------------------------------------------------------------
 

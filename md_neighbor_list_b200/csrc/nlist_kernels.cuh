@@ -1297,6 +1297,52 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(const T* __restrict__ q,
   out_gid[p] = gids != nullptr ? gids[i] : gid_base + (int32_t)i;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// callers either side of the build
+// ---------------------------------------------------------------------------------------------------------------
+// f2, Verlet-list lifetime: the search length includes a margin (make_list.cpp:23: 3.0 + 0.3) so that a list stays
+// valid until some particle has moved more than margin/2 since the build.  max |q_now - q_ref|^2 over the particles;
+// the block maxima are combined with an atomicMax on the bit pattern (non-negative doubles order like integers).
+template <typename T>
+__global__ void __launch_bounds__(256) max_disp2_kernel(const T* __restrict__ q, const T* __restrict__ qref,
+                                                        int64_t n, int stride,
+                                                        unsigned long long* __restrict__ out_bits) {
+  double m = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double dx = (double)q[i * stride] - (double)qref[i * stride];
+    const double dy = (double)q[i * stride + 1] - (double)qref[i * stride + 1];
+    const double dz = (double)q[i * stride + 2] - (double)qref[i * stride + 2];
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    m = d2 > m ? d2 : m;  // NaN never wins; bin_kernel reports NaN positions at the next build
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double o = __shfl_xor_sync(0xffffffffu, m, d);
+    m = o > m ? o : m;
+  }
+  __shared__ double wm[8];
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; k++) m = wm[k] > m ? wm[k] : m;
+    atomicMax(out_bits, (unsigned long long)__double_as_longlong(m));
+  }
+}
+
+// f1, the physical reorder the reference stubbed out (SortPtclData, neighlist_cpu.hpp:176-180; CopyGather,
+// neighlist_gpu.hpp:144-151): out[slot] = src[sorted_ids[slot]] for any per-particle array of `width` elements.
+template <typename T>
+__global__ void __launch_bounds__(256) gather_sorted_kernel(const T* __restrict__ src,
+                                                            const int32_t* __restrict__ sorted_ids,
+                                                            const int32_t* __restrict__ n_present, int width,
+                                                            T* __restrict__ dst) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t slot = t / width;
+  if (slot >= *n_present) return;
+  const int c = (int)(t - slot * width);
+  dst[t] = src[(int64_t)sorted_ids[slot] * width + c];
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) gather_records_kernel(const T* __restrict__ src,
                                                              const int32_t* __restrict__ idx, int64_t count,

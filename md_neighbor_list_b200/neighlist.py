@@ -140,6 +140,31 @@ class VerletListB200:
             out_t.copy_(t)
         return out[:total]
 
+    # -- callers either side of the build -----------------------------------------------------------
+    def track(self, q: torch.Tensor, stream: torch.cuda.Stream | None = None) -> None:
+        """Remember the positions the current list was built from (Verlet-list lifetime, nlb200_track_reference)."""
+        s = stream if stream is not None else torch.cuda.current_stream()
+        check(self._h, self._lib.nlb200_track_reference(self._h, q.data_ptr(), q.shape[0], s.cuda_stream))
+
+    def max_displacement(self, q: torch.Tensor, stream: torch.cuda.Stream | None = None) -> float:
+        """max_i |q[i] - q_tracked[i]|: rebuild when it exceeds margin / 2."""
+        s = stream if stream is not None else torch.cuda.current_stream()
+        out = C.c_double(0.0)
+        check(self._h, self._lib.nlb200_max_displacement(self._h, q.data_ptr(), q.shape[0], s.cuda_stream,
+                                                         C.byref(out)))
+        return float(out.value)
+
+    def gather_sorted(self, src: torch.Tensor, stream: torch.cuda.Stream | None = None) -> torch.Tensor:
+        """src[sorted_ids] for a per-particle CUDA array (n, width) of 4- or 8-byte elements: the cell-ordered copy
+        the reference stubbed out (SortPtclData / CopyGather)."""
+        s = stream if stream is not None else torch.cuda.current_stream()
+        src = src.contiguous()
+        width = 1 if src.dim() == 1 else src.shape[1]
+        dst = torch.empty_like(src)
+        check(self._h, self._lib.nlb200_gather_sorted(self._h, src.data_ptr(), src.element_size(), width,
+                                                      dst.data_ptr(), s.cuda_stream))
+        return dst
+
     # -- accessors ------------------------------------------------------------------------------------------------
     def stats(self) -> Stats:
         s = Stats()

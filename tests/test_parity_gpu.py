@@ -548,3 +548,41 @@ def test_cpp_driver_self_test(cuda, iface, dens):
     assert r.returncode == 0, r.stderr
     assert "TEST is passed." in r.stderr
     assert "# of particles 62500" in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# callers either side of the build
+# ---------------------------------------------------------------------------------------------------------------
+def test_displacement_tracking_and_cell_ordered_gather(cuda, oracle):
+    from md_neighbor_list_b200 import VerletListB200, workloads
+    torch = cuda
+    L, SL, margin = 24.0, 3.3, 0.3
+    q = workloads.fcc(1.0, L)
+    n = q.shape[0]
+    qd = torch.from_numpy(q).cuda()
+    nl = VerletListB200(SL, L, L, L, mode="half_csr")
+    nl.initialize(n)
+    nl.build(qd)
+    nl.track(qd)
+    nl.synchronize()
+    assert nl.max_displacement(qd) == 0.0
+    rng = np.random.default_rng(5)
+    d = (rng.random((n, 3)) - 0.5) * 0.1
+    q2 = q.copy()
+    q2[:, :3] += d
+    want = float(np.sqrt(((q2[:, :3] - q[:, :3]) ** 2).sum(axis=1).max()))
+    got = nl.max_displacement(torch.from_numpy(q2).cuda())
+    assert abs(got - want) <= 1e-15 * max(1.0, want)
+    assert got < margin / 2  # the list built from q is still complete for rc = 3.0 at q2
+    # every pair within rc = SL - margin at q2 is in the list built at q
+    ref_now = oracle.build_half(q2, SL - margin, (L, L, L)).sorted_rows()
+    off = nl.offsets().cpu().numpy()
+    lst = sort_rows(oracle, nl.partners().cpu().numpy(), off)
+    for i in range(0, n, 53):
+        have = set(lst[off[i]:off[i + 1]].tolist())
+        assert set(ref_now.partners[ref_now.offsets[i]:ref_now.offsets[i + 1]].tolist()) <= have
+    # cell-ordered copies of per-particle arrays
+    ids = nl.sorted_ids().cpu().numpy()
+    assert np.array_equal(nl.gather_sorted(qd).cpu().numpy(), q[ids])
+    v32 = torch.arange(n, dtype=torch.float32, device="cuda") * 0.5
+    assert np.array_equal(nl.gather_sorted(v32).cpu().numpy(), (np.arange(n, dtype=np.float32) * 0.5)[ids])
