@@ -1056,25 +1056,19 @@ int nlb200_pack_slab2(const void* q_dev, const int32_t* gids_dev, int64_t n, int
                       int64_t workspace_bytes, void* stream) {
   if (n < 0 || capacity < 0 || axis < 0 || axis > 2 || (stride != 3 && stride != 4)) return NLB200_ERR_INVALID;
   const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE + 1;
+  // workspace: [flags_lo | pos_lo] [flags_hi | pos_hi] [scan state lo | scan state hi]
   const size_t o_pos = align_up(sizeof(int32_t) * (size_t)(n + 8), 256);
-  const size_t o_state = align_up(o_pos + sizeof(int64_t) * (size_t)(n + 1), 256);
-  const size_t half = align_up(o_state + sizeof(unsigned long long) * (size_t)(tiles + 2), 256);
-  if (workspace_dev == nullptr || (size_t)workspace_bytes < 2 * half) return NLB200_ERR_CAPACITY;
+  const size_t blk = align_up(o_pos + sizeof(int64_t) * (size_t)(n + 1), 256);
+  const size_t st_sz = align_up(sizeof(unsigned long long) * (size_t)(tiles + 2), 256);
+  if (workspace_dev == nullptr || (size_t)workspace_bytes < 2 * blk + 2 * st_sz) return NLB200_ERR_CAPACITY;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace_dev);
-  int32_t* flags[2] = {reinterpret_cast<int32_t*>(ws), reinterpret_cast<int32_t*>(ws + half)};
-  int64_t* pos[2] = {reinterpret_cast<int64_t*>(ws + o_pos), reinterpret_cast<int64_t*>(ws + half + o_pos)};
-  unsigned long long* state[2] = {reinterpret_cast<unsigned long long*>(ws + o_state),
-                                  reinterpret_cast<unsigned long long*>(ws + half + o_state)};
-  const size_t esz = dtype == NLB200_F64 ? 8 : 4;
-  void* outs[2] = {out_q_lo_dev, out_q_hi_dev};
-  for (int f = 0; f < 2; f++) {
-    // all-ones bytes are a NaN in both precisions: every slot starts as an absent ghost
-    if (outs[f] && capacity > 0 && cudaMemsetAsync(outs[f], 0xFF, (size_t)capacity * stride * esz, s) != cudaSuccess)
-      return NLB200_ERR_CUDA;
-    if (cudaMemsetAsync(state[f], 0, sizeof(unsigned long long) * (size_t)(tiles + 2), s) != cudaSuccess)
-      return NLB200_ERR_CUDA;
-  }
+  int32_t* flags[2] = {reinterpret_cast<int32_t*>(ws), reinterpret_cast<int32_t*>(ws + blk)};
+  int64_t* pos[2] = {reinterpret_cast<int64_t*>(ws + o_pos), reinterpret_cast<int64_t*>(ws + blk + o_pos)};
+  unsigned long long* state[2] = {reinterpret_cast<unsigned long long*>(ws + 2 * blk),
+                                  reinterpret_cast<unsigned long long*>(ws + 2 * blk + st_sz)};
+  // one memset clears both look-back states; the NaN padding of the unused slots is written by the packing kernel
+  if (cudaMemsetAsync(state[0], 0, 2 * st_sz, s) != cudaSuccess) return NLB200_ERR_CUDA;
   const unsigned g = (unsigned)((n + 255) / 256);
   if (n > 0) {
     if (dtype == NLB200_F64)
@@ -1087,12 +1081,14 @@ int nlb200_pack_slab2(const void* q_dev, const int32_t* gids_dev, int64_t n, int
   for (int f = 0; f < 2; f++)
     scan_kernel<int64_t><<<(unsigned)(tiles - 1 > 0 ? tiles - 1 : 1), SCAN_THREADS, 0, s>>>(
         flags[f], n, pos[f], nullptr, state[f], nullptr, nullptr, 0);
+  const int64_t span = n > capacity ? n : capacity;
+  const unsigned gp = (unsigned)((span + 255) / 256 > 0 ? (span + 255) / 256 : 1);
   if (dtype == NLB200_F64)
-    slab_pack2_kernel<double><<<g > 0 ? g : 1, 256, 0, s>>>(
+    slab_pack2_kernel<double><<<gp, 256, 0, s>>>(
         (const double*)q_dev, gids_dev, flags[0], pos[0], flags[1], pos[1], n, stride, (double*)out_q_lo_dev,
         out_gid_lo_dev, (double*)out_q_hi_dev, out_gid_hi_dev, capacity, out_counts_dev);
   else
-    slab_pack2_kernel<float><<<g > 0 ? g : 1, 256, 0, s>>>(
+    slab_pack2_kernel<float><<<gp, 256, 0, s>>>(
         (const float*)q_dev, gids_dev, flags[0], pos[0], flags[1], pos[1], n, stride, (float*)out_q_lo_dev,
         out_gid_lo_dev, (float*)out_q_hi_dev, out_gid_hi_dev, capacity, out_counts_dev);
   return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;

@@ -1270,6 +1270,12 @@ __global__ void __launch_bounds__(256) slab_pack2_kernel(const T* __restrict__ q
     out_counts[0] = pos_lo[n];
     out_counts[1] = pos_hi[n];
   }
+  // slots behind the selected records become ABSENT ghosts (NaN x); the grid covers max(n, capacity) threads
+  if (i < capacity) {
+    const T nan = (T)__longlong_as_double(0x7ff8000000000000ll);
+    if (out_q_lo != nullptr && i >= pos_lo[n]) out_q_lo[i * stride] = nan;
+    if (out_q_hi != nullptr && i >= pos_hi[n]) out_q_hi[i * stride] = nan;
+  }
   if (i >= n) return;
   const bool lo = flags_lo[i] != 0 && out_q_lo != nullptr, hi = flags_hi[i] != 0 && out_q_hi != nullptr;
   if (!lo && !hi) return;

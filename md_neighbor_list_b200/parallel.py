@@ -195,8 +195,6 @@ class SlabDecomposition:
             at += cap
         for r in dist.batch_isend_irecv(ops):
             r.wait()
-        for p in peers:
-            self._cnt_host[p].copy_(self._cnt[p], non_blocking=True)
         self._last = (self._qall, self._gall, n)
         return self._last
 
@@ -216,7 +214,7 @@ class SlabDecomposition:
         returns the ghosts sent (below, above)."""
         sent = []
         for p in (self.rank - 1, self.rank + 1):
-            c = int(self._cnt_host[p][0]) if (self._cnt_host is not None and p in self._cnt_host) else 0
+            c = int(self._cnt[p][0]) if (self._cnt is not None and p in self._cnt) else 0  # small D2H, synchronises
             if c > (self._cap or 0):
                 raise _lib.NlistError(_lib.ERR_CAPACITY,
                                       f"{c} ghosts for rank {p} exceed the face capacity {self._cap}: raise `slack`")
