@@ -209,6 +209,13 @@ int nlb200_max_displacement(nlb200_handle h, const void* q_dev, int64_t n, void*
  * elem_bytes (4 or 8) each, in the cell order of the last build — lets a downstream kernel read coalesced. */
 int nlb200_gather_sorted(nlb200_handle h, const void* src_dev, int elem_bytes, int width, void* dst_dev, void* stream);
 
+/* f4, a consumer of the list: Lennard-Jones forces f[n][3] (and, if energy_dev != NULL, per-particle energies whose
+ * sum is the total) over the FULL rows of the last build, cutoff rc <= search length, plain Euclidean distance like the
+ * list.  The reference allocates the momenta `p` and never uses them (make_list.cpp:135-140); this closes the loop:
+ * list quality end to end, and the build-versus-use cost. */
+int nlb200_lj_forces(nlb200_handle h, const void* q_dev, double rc, double epsilon, double sigma, double* forces_dev,
+                     double* energy_dev, void* stream);
+
 /* ---- adjacent utilities (device side of the drivers) ---------------------------------------------------------- */
 
 /* Ghost selection for slab decomposition: writes the indices i < n with lo <= q[i][axis] < hi into

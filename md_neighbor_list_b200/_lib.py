@@ -57,6 +57,7 @@ SYMBOLS = {
     "nlb200_last_error": (C.c_char_p, [_vp]),
     "nlb200_track_reference": (C.c_int, [_vp, _vp, _i64, _vp]),
     "nlb200_max_displacement": (C.c_int, [_vp, _vp, _i64, _vp, C.POINTER(_dbl)]),
+    "nlb200_lj_forces": (C.c_int, [_vp, _vp, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
     "nlb200_gather_sorted": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "nlb200_select_slab": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _dbl, _dbl, _vp, _i64, _vp, _vp, _i64, _vp]),
     "nlb200_pack_slab": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _i32, _dbl, _dbl, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),

@@ -41,7 +41,7 @@ struct nlb200_context {
   unsigned long long* scan_state_cells = nullptr;
   unsigned long long* scan_state_counts = nullptr;
   DeviceStatus* status_dev = nullptr;
-  int32_t* queue = nullptr;  // work counter of the persistent pair-mask kernel (inside zero_region)
+  unsigned long long* queue = nullptr;  // work counter of the persistent pair-mask kernel (inside zero_region)
   int sm_count = 148;
   int64_t l2_bytes = 0;
   int32_t* cell_start = nullptr;
@@ -627,14 +627,14 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
   const size_t o_st = off;
   off = align_up(off + sizeof(DeviceStatus), 256);
   const size_t o_q = off;
-  off = align_up(off + sizeof(int32_t), 256);
+  off = align_up(off + sizeof(unsigned long long), 256);
   h->zero_bytes = off;
   CK(h, cudaMalloc(&h->zero_region, off));
   h->cell_count = reinterpret_cast<int32_t*>(h->zero_region + o_count);
   h->scan_state_cells = reinterpret_cast<unsigned long long*>(h->zero_region + o_sc);
   h->scan_state_counts = reinterpret_cast<unsigned long long*>(h->zero_region + o_sn);
   h->status_dev = reinterpret_cast<DeviceStatus*>(h->zero_region + o_st);
-  h->queue = reinterpret_cast<int32_t*>(h->zero_region + o_q);
+  h->queue = reinterpret_cast<unsigned long long*>(h->zero_region + o_q);
   CK(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
   {
     int l2 = 0;
@@ -954,6 +954,28 @@ int nlb200_max_displacement(nlb200_handle h, const void* q_dev, int64_t n, void*
   double d2;
   memcpy(&d2, h->disp_host, sizeof(double));
   *max_disp_host = std::sqrt(d2);
+  return NLB200_OK;
+}
+
+int nlb200_lj_forces(nlb200_handle h, const void* q_dev, double rc, double epsilon, double sigma, double* forces_dev,
+                     double* energy_dev, void* stream) {
+  if (!h) return NLB200_ERR_INVALID;
+  if (!h->initialized || (!h->build_pending && !h->have_result))
+    return fail(h, NLB200_ERR_STATE, "lj_forces needs a build");
+  if (h->mode == NLB200_HALF_CSR) return fail(h, NLB200_ERR_INVALID, "lj_forces reads FULL rows");
+  if (!(rc > 0) || rc > h->sl || !q_dev || !forces_dev)
+    return fail(h, NLB200_ERR_INVALID, "lj_forces: 0 < rc <= search length, non-null buffers");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int32_t n = (int32_t)h->last_owned;
+  if (n == 0) return NLB200_OK;
+  const unsigned g = (unsigned)(((int64_t)n * 32 + 127) / 128);
+  if (h->dtype == NLB200_F64)
+    lj_forces_kernel<double><<<g, 128, 0, s>>>((const double*)q_dev, h->stride, n, h->offsets, h->partners, rc * rc,
+                                               epsilon, sigma * sigma, forces_dev, energy_dev);
+  else
+    lj_forces_kernel<float><<<g, 128, 0, s>>>((const float*)q_dev, h->stride, n, h->offsets, h->partners, rc * rc,
+                                              epsilon, sigma * sigma, forces_dev, energy_dev);
+  CK(h, cudaGetLastError());
   return NLB200_OK;
 }
 

@@ -597,7 +597,7 @@ struct PairMaskArgs {
   long long n_cap;
   int32_t wi;
   float band;
-  int32_t* queue;   // item counter (zeroed per build): warps draw (cell, part) items from it
+  unsigned long long* queue;  // item counter (zeroed per build): warps draw (cell, part) items from it
   int32_t parts;   // items per cell: part p takes the candidate chunks p, p + parts, ...  (small systems: more
                    // items than resident warps, so that the queue can balance them)
   int32_t grab;    // items drawn per atomic (large systems: the single counter would otherwise serialise the warps)
@@ -638,14 +638,16 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
   unsigned long long band_local = 0, cand_local = 0;
 
   const long long n_items = (long long)gp.n_cells * a.parts;
-  int32_t base = 0;
-  if (lane == 0) base = atomicAdd(a.queue, a.grab);
-  base = __shfl_sync(0xffffffffu, base, 0);
+  // the first batch of every warp is static (no storm of atomics on one address at start-up); later batches come from
+  // the queue, which therefore starts behind the static ones
+  const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long first_dyn = n_warps * a.grab;
+  long long base = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * a.grab;
   while (base < n_items) {
-    int32_t next = 0;
-    if (lane == 0) next = atomicAdd(a.queue, a.grab);  // in flight while this batch is processed
-    for (int32_t item = base; item < base + a.grab && item < n_items; item++) {
-    const int32_t cell = item / a.parts, part = item - cell * a.parts;
+    long long next = 0;
+    if (lane == 0) next = first_dyn + (long long)atomicAdd(a.queue, (unsigned long long)a.grab);  // in flight meanwhile
+    for (long long item = base; item < base + a.grab && item < n_items; item++) {
+    const int32_t cell = (int32_t)(item / a.parts), part = (int32_t)(item - (long long)cell * a.parts);
     const int32_t ibeg = __ldg(a.cell_start + cell);
     int32_t ni = __ldg(a.cell_start + cell + 1) - ibeg;
     if (ni > 0) {
@@ -1342,6 +1344,52 @@ __global__ void __launch_bounds__(256) max_disp2_kernel(const T* __restrict__ q,
   if (threadIdx.x == 0) {
     for (int k = 1; k < 8; k++) m = wm[k] > m ? wm[k] : m;
     atomicMax(out_bits, (unsigned long long)__double_as_longlong(m));
+  }
+}
+
+// f4, a consumer of the list: Lennard-Jones forces and energy over the FULL CSR rows (the reference allocates a
+// momentum array `p` it never uses, make_list.cpp:135-140).  One warp per row: lanes stride over the partners (coalesced
+// reads of the row, gathered partner positions), warp-reduce, lane 0 writes.  Pairs beyond rc contribute nothing —
+// the list is built with rc + margin.  Plain Euclidean distance, like the list itself.
+template <typename T>
+__global__ void __launch_bounds__(128) lj_forces_kernel(const T* __restrict__ q, int stride, int32_t n,
+                                                        const int64_t* __restrict__ offsets,
+                                                        const int32_t* __restrict__ partners, double rc2, double eps,
+                                                        double sigma2, double* __restrict__ f,
+                                                        double* __restrict__ energy) {
+  const int32_t i = (int32_t)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (i >= n) return;
+  const int lane = lane_id();
+  const double xi = (double)q[(int64_t)i * stride], yi = (double)q[(int64_t)i * stride + 1],
+               zi = (double)q[(int64_t)i * stride + 2];
+  double fx = 0, fy = 0, fz = 0, e = 0;
+  const int64_t beg = offsets[i], end = offsets[i + 1];
+  for (int64_t k = beg + lane; k < end; k += 32) {
+    const int32_t j = partners[k];
+    const double dx = xi - (double)q[(int64_t)j * stride], dy = yi - (double)q[(int64_t)j * stride + 1],
+                 dz = zi - (double)q[(int64_t)j * stride + 2];
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    if (r2 < rc2 && r2 > 0.0) {
+      const double s2 = sigma2 / r2, s6 = s2 * s2 * s2;
+      const double fr = 24.0 * eps * s6 * (2.0 * s6 - 1.0) / r2;  // -(dU/dr)/r
+      fx += fr * dx;
+      fy += fr * dy;
+      fz += fr * dz;
+      e += 2.0 * eps * s6 * (s6 - 1.0);  // half of 4 eps (s12 - s6): every pair appears in two rows
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    fx += __shfl_xor_sync(0xffffffffu, fx, d);
+    fy += __shfl_xor_sync(0xffffffffu, fy, d);
+    fz += __shfl_xor_sync(0xffffffffu, fz, d);
+    e += __shfl_xor_sync(0xffffffffu, e, d);
+  }
+  if (lane == 0) {
+    f[(int64_t)i * 3] = fx;
+    f[(int64_t)i * 3 + 1] = fy;
+    f[(int64_t)i * 3 + 2] = fz;
+    if (energy != nullptr) energy[i] = e;
   }
 }
 

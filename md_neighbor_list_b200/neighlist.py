@@ -154,6 +154,16 @@ class VerletListB200:
                                                          C.byref(out)))
         return float(out.value)
 
+    def lj_forces(self, q: torch.Tensor, rc: float, epsilon: float = 1.0, sigma: float = 1.0,
+                  stream: torch.cuda.Stream | None = None):
+        """(forces (n, 3), per-particle energies (n,)) of a Lennard-Jones fluid over the FULL rows of the last build."""
+        s = stream if stream is not None else torch.cuda.current_stream()
+        f = torch.empty((self.n, 3), dtype=torch.float64, device=q.device)
+        e = torch.empty(self.n, dtype=torch.float64, device=q.device)
+        check(self._h, self._lib.nlb200_lj_forces(self._h, q.data_ptr(), rc, epsilon, sigma, f.data_ptr(),
+                                                  e.data_ptr(), s.cuda_stream))
+        return f, e
+
     def gather_sorted(self, src: torch.Tensor, stream: torch.cuda.Stream | None = None) -> torch.Tensor:
         """src[sorted_ids] for a per-particle CUDA array (n, width) of 4- or 8-byte elements: the cell-ordered copy
         the reference stubbed out (SortPtclData / CopyGather)."""

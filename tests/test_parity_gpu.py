@@ -586,3 +586,39 @@ def test_displacement_tracking_and_cell_ordered_gather(cuda, oracle):
     assert np.array_equal(nl.gather_sorted(qd).cpu().numpy(), q[ids])
     v32 = torch.arange(n, dtype=torch.float32, device="cuda") * 0.5
     assert np.array_equal(nl.gather_sorted(v32).cpu().numpy(), (np.arange(n, dtype=np.float32) * 0.5)[ids])
+
+
+def test_lennard_jones_consumer_matches_numpy(cuda, oracle):
+    """SURVEY.md §8f f4: forces and energy over the FULL list equal an O(N^2) numpy evaluation with the same cutoff;
+    a list built with the margin still gives the exact forces after the particles moved less than margin / 2."""
+    from md_neighbor_list_b200 import VerletListB200, workloads
+    torch = cuda
+    L, rc, margin = 13.0, 3.0, 0.3
+    q = workloads.fcc(1.0, L)
+    n = q.shape[0]
+
+    def reference(p):
+        d = p[:, None, :3] - p[None, :, :3]
+        r2 = (d ** 2).sum(-1)
+        m = (r2 < rc * rc) & (r2 > 0)
+        s6 = np.where(m, 1.0 / np.where(m, r2, 1.0) ** 3, 0.0)
+        fr = np.where(m, 24.0 * s6 * (2.0 * s6 - 1.0) / np.where(m, r2, 1.0), 0.0)
+        return (fr[:, :, None] * d).sum(1), float((4.0 * s6 * (s6 - 1.0)).sum() / 2)
+
+    nl = VerletListB200(rc + margin, L, L, L, mode="full_csr")
+    nl.initialize(n)
+    qd = torch.from_numpy(q).cuda()
+    nl.build(qd)
+    nl.synchronize()
+    f, e = nl.lj_forces(qd, rc)
+    fr, er = reference(q)
+    assert np.allclose(f.cpu().numpy(), fr, rtol=1e-11, atol=1e-11)
+    assert abs(float(e.sum()) - er) <= 1e-10 * abs(er)
+    assert np.abs(f.cpu().numpy().sum(0)).max() < 1e-9  # Newton's third law through the symmetric list
+    # moved by less than margin / 2: the old list is still complete for rc
+    q2 = q.copy()
+    q2[:, :3] += (np.random.default_rng(7).random((n, 3)) - 0.5) * 0.15
+    f2, e2 = nl.lj_forces(torch.from_numpy(q2).cuda(), rc)
+    fr2, er2 = reference(q2)
+    assert np.allclose(f2.cpu().numpy(), fr2, rtol=1e-11, atol=1e-11)
+    assert abs(float(e2.sum()) - er2) <= 1e-10 * abs(er2)
