@@ -3,7 +3,8 @@ list-build path).  The product is libnlist_b200.so (hand-written sm_100a CUDA be
 include/nlist_b200.h); this package is the thin host-side mirror of the reference's class interface."""
 from ._lib import (F32, F64, FULL_CSR, FULL_ELL_TRANSPOSED, HALF_CSR, LIB_PATH, NlistError, Stats, SYMBOLS)  # noqa: F401
 
-__all__ = ["VerletListB200", "NeighListGPU", "NeighList", "workloads", "NlistError", "LIB_PATH", "SYMBOLS"]
+__all__ = ["VerletListB200", "NeighListGPU", "NeighList", "PeriodicVerletList", "workloads", "NlistError", "LIB_PATH",
+           "SYMBOLS"]
 
 
 def __getattr__(name):
@@ -11,6 +12,8 @@ def __getattr__(name):
     import importlib
     if name in ("VerletListB200", "NeighListGPU", "NeighList"):
         return getattr(importlib.import_module(__name__ + ".neighlist"), name)
-    if name in ("workloads", "neighlist"):
+    if name == "PeriodicVerletList":
+        return getattr(importlib.import_module(__name__ + ".periodic"), name)
+    if name in ("workloads", "neighlist", "parallel", "periodic"):
         return importlib.import_module(__name__ + "." + name)
     raise AttributeError(name)

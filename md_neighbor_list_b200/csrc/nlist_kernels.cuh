@@ -1275,8 +1275,11 @@ __global__ void __launch_bounds__(256) slab_pack2_kernel(const T* __restrict__ q
   // slots behind the selected records become ABSENT ghosts (NaN x); the grid covers max(n, capacity) threads
   if (i < capacity) {
     const T nan = (T)__longlong_as_double(0x7ff8000000000000ll);
-    if (out_q_lo != nullptr && i >= pos_lo[n]) out_q_lo[i * stride] = nan;
-    if (out_q_hi != nullptr && i >= pos_hi[n]) out_q_hi[i * stride] = nan;
+    // every component: an absent record must fail any later coordinate test (periodic images are built axis by axis)
+    for (int c = 0; c < stride; c++) {
+      if (out_q_lo != nullptr && i >= pos_lo[n]) out_q_lo[i * stride + c] = nan;
+      if (out_q_hi != nullptr && i >= pos_hi[n]) out_q_hi[i * stride + c] = nan;
+    }
   }
   if (i >= n) return;
   const bool lo = flags_lo[i] != 0 && out_q_lo != nullptr, hi = flags_hi[i] != 0 && out_q_hi != nullptr;

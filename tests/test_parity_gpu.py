@@ -622,3 +622,36 @@ def test_lennard_jones_consumer_matches_numpy(cuda, oracle):
     fr2, er2 = reference(q2)
     assert np.allclose(f2.cpu().numpy(), fr2, rtol=1e-11, atol=1e-11)
     assert abs(float(e2.sum()) - er2) <= 1e-10 * abs(er2)
+
+
+@pytest.mark.parametrize("mode", ["full_csr", "half_csr"])
+def test_periodic_minimum_image(cuda, mode):
+    """periodic images as ghost records -> rows = minimum-image neighbours (numpy brute force)."""
+    from md_neighbor_list_b200 import PeriodicVerletList
+    torch = cuda
+    rng = np.random.default_rng(11)
+    n, L, SL = 3000, (21.0, 17.5, 14.0), 3.3
+    q = np.zeros((n, 4))
+    q[:, :3] = rng.random((n, 3)) * np.array(L)
+    q[:40, 0] = 0.0                      # on the lower wall
+    q[40:80, 1] = np.nextafter(L[1], 0)  # just inside the upper wall
+    pl = PeriodicVerletList(SL, *L, mode=mode)
+    pl.initialize(n)
+    qd = torch.from_numpy(q).cuda()
+    pl.build(qd)
+    pl.build(qd)  # graph replay
+    st = pl.synchronize()
+    d = q[:, None, :3] - q[None, :, :3]
+    d -= np.array(L) * np.round(d / np.array(L))
+    r2 = (d ** 2).sum(-1)
+    hit = r2 <= SL * SL
+    np.fill_diagonal(hit, False)
+    if mode == "half_csr":
+        hit &= np.arange(n)[None, :] > np.arange(n)[:, None]
+    cnt = pl.number_of_partners().cpu().numpy()
+    off = pl.offsets().cpu().numpy()
+    lst = pl.partners().cpu().numpy()
+    assert np.array_equal(cnt, hit.sum(1))
+    assert st.number_of_pairs == int(hit.sum())
+    for i in range(n):
+        assert np.array_equal(np.sort(lst[off[i]:off[i + 1]]), np.nonzero(hit[i])[0])
