@@ -553,7 +553,10 @@ __global__ void __launch_bounds__(128) search_kernel(SearchArgs<T> a) {
 #define NLB_PM_RJ 8
 #endif
 constexpr int PM_RJ = NLB_PM_RJ;  // candidates per lane (packed in pairs)
-constexpr int PM_THREADS = 128;  // 4 warps per cell
+#ifndef NLB_PM_THREADS
+#define NLB_PM_THREADS 128
+#endif
+constexpr int PM_THREADS = NLB_PM_THREADS;  // warps are independent; the CTA only groups them
 constexpr uint32_t FLAG_CELL_WORDS = 16u;  // a cell holds more than 32*WI particles: mask words too narrow
 
 __device__ __forceinline__ int axis_lo(int c, int m) { return m == 3 ? 0 : max(c - 1, 0); }
@@ -954,8 +957,14 @@ __global__ void __launch_bounds__(128) emit_direct_kernel(EmitArgs a) {
 //   resident; the expansion is a chain of dependent ALU/XU ops and needs that many to hide its latency.
 // HALF:  rows keep the partners with a larger (global) id (neighlist_cpu.hpp:225-236); the filter runs in the flush
 //        (ballot compaction).  COUNT: write counts[id] instead of partners (HALF lists need the ids to count).
-constexpr int EM_WARPS = 4;
-constexpr int EM_TILE = 64;
+#ifndef NLB_EM_WARPS
+#define NLB_EM_WARPS 2
+#endif
+constexpr int EM_WARPS = NLB_EM_WARPS;
+#ifndef NLB_EM_TILE
+#define NLB_EM_TILE 56
+#endif
+constexpr int EM_TILE = NLB_EM_TILE;
 constexpr int EM_LINE = EM_TILE + 1;  // +1: lanes with equal fill hit different banks
 
 template <bool HALF, bool GID, bool COUNT>
