@@ -409,9 +409,9 @@ def run_ours(args):
                              f"(the reference is single-threaded); ms/build: "
                              + ", ".join(f"{k}={v:.1f}" for k, v in times.items()),
                    "ms_per_build": times, "host_nproc": os.cpu_count()}
-        # kernels of one build: bin, scan(cells), scatter, cellsort, pairmask, scan(counts), emit
-        # (+ select/gather x2 per face in the multi-GPU halo)
-        kernels_per_build = 7 if world == 1 else 7 + 8
+        # kernels of one build: bin, scan(cells), scatter, cellsort, pairmask, rowcount, scan(counts), emit
+        # (+ the halo packing of a slab rank: flag, 2 scans, pack)
+        kernels_per_build = 8 if world == 1 else 8 + 4
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
