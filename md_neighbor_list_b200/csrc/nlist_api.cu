@@ -252,7 +252,11 @@ cudaError_t set_emit_attr() {
 
 template <typename T, int STRIDE>
 cudaError_t set_pm_attr() {
-  return cudaFuncSetAttribute(pairmask_kernel<T, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(pairmask_kernel<T, STRIDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       MAX_EMIT_SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(pairmask_kernel<T, STRIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              MAX_EMIT_SMEM);
 }
 
 cudaError_t set_search_attrs() {
@@ -407,6 +411,7 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     em.n_total = n;
     em.n_owned = (int32_t)n_owned;
     em.n_cells = M;
+    em.clear_self = half ? 0 : 1;
     em.mask = h->mask;
     em.n_cap = h->mask_ncap;
     em.wi = h->mask_wi;
@@ -415,12 +420,21 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     em.partners = h->partners;
     em.capacity = h->cap_entries;
     const bool direct = h->variant == 3;  // ablation: per-thread scalar stores instead of the staged emission
+    // HALF lists without a global-id map: the id filter is folded into the masks (pairmask_kernel<HALFIDS>), so the
+    // popcount pass and the plain emission serve; with a map (multi-GPU) or as variant 4 the emission filters by id
+    const bool half_in_mask = half && gids == nullptr && h->variant != 4;
+    const bool half_emit = half && !half_in_mask;
     CK(h, stage(ST_PAIRMASK));
     if (n > 0) {
       // persistent warps: as many CTAs as are resident at once, each warp draws cells from the queue
       const size_t pm_smem = pm_warp_bytes(h->mask_wi) * (PM_THREADS / 32);
       int per_sm = 0;
-      CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairmask_kernel<T, STRIDE>, PM_THREADS, pm_smem));
+      if (half_in_mask)
+        CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairmask_kernel<T, STRIDE, true>, PM_THREADS,
+                                                            pm_smem));
+      else
+        CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairmask_kernel<T, STRIDE, false>, PM_THREADS,
+                                                            pm_smem));
       if (per_sm < 1) per_sm = 1;
       int64_t grid = (int64_t)per_sm * h->sm_count;
       // items per cell: at least ~4 items per resident warp so that the queue can balance a small system
@@ -437,12 +451,15 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
       pm.grab = (int32_t)grab;
       const int64_t need = (M * parts + PM_THREADS / 32 - 1) / (PM_THREADS / 32);
       if (grid > need) grid = need;
-      pairmask_kernel<T, STRIDE><<<(unsigned)grid, PM_THREADS, pm_smem, s>>>(pm);
+      if (half_in_mask)
+        pairmask_kernel<T, STRIDE, true><<<(unsigned)grid, PM_THREADS, pm_smem, s>>>(pm);
+      else
+        pairmask_kernel<T, STRIDE, false><<<(unsigned)grid, PM_THREADS, pm_smem, s>>>(pm);
       CK(h, cudaGetLastError());
     }
     CK(h, stage(ST_ROWCOUNT));
     if (n > 0) {
-      if (half) {
+      if (half_emit) {
         CK(h, launch_emit(true, true, direct, em, s));  // HALF rows need the ids to count
       } else {
         rowcount_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(em);
@@ -458,7 +475,7 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
       CK(h, cudaGetLastError());
     }
     CK(h, stage(ST_EMIT));
-    if (n > 0) CK(h, launch_emit(half, false, direct, em, s));
+    if (n > 0) CK(h, launch_emit(half_emit, false, direct, em, s));
   }
   if (h->sort_rows) CK(h, stage(ST_SORT_ROWS));
   if (h->sort_rows && n_owned > 0) {

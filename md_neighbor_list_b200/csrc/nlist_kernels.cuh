@@ -620,7 +620,11 @@ __host__ __device__ inline size_t pm_warp_bytes(int wi) {
 #ifndef NLB_PM_MINB
 #define NLB_PM_MINB 4
 #endif
-template <typename T, int STRIDE>
+// HALFIDS: HALF lists without a global-id map.  Row j keeps the partners with a larger id (neighlist_cpu.hpp:225-236).
+// The ids of a cell ascend with the slot, so inside one cell these partners are a SUFFIX: the first kept particle is
+// found once per (candidate, cell) by a binary search and every word is cut with one AND — the filter costs nothing
+// per test, the popcount pass and the emission then see HALF rows directly.
+template <typename T, int STRIDE, bool HALFIDS>
 __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairMaskArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -724,6 +728,7 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
         float xj[PM_RJ], yj[PM_RJ], zj[PM_RJ], wj[PM_RJ];
         int32_t sj[PM_RJ];  // candidate's slot
         int32_t oj[PM_RJ];  // its mask plane for this cell (o * wi); -1: tail lane or ghost row, nothing to store
+        int32_t pj[PM_RJ];  // HALFIDS: particles of this cell with an id <= the candidate's (they are not kept)
         int r = 0;
 #pragma unroll
         for (int k = 0; k < PM_RJ; k++) {
@@ -732,6 +737,7 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
           wj[k] = -1.0e30f;  // d = -1e30: a miss, far from the band
           sj[k] = 0;
           oj[k] = -1;
+          pj[k] = 0;
           if (c < nj) {
             while (c >= t_pre[r + 1]) r++;
             const int32_t s = t_start[r] + (c - t_pre[r]);
@@ -743,7 +749,20 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
             wj[k] = -0.5f * fmaf(xj[k], xj[k], fmaf(yj[k], yj[k], zj[k] * zj[k]));
             sj[k] = s;
             // rec.w carries the particle's local id (cellsort_kernel): rows of ghosts (id >= n_owned) are not stored
-            if (__float_as_int(rj.w) < a.n_owned) oj[k] = (t_o[r] + (col == 0 ? oxs[0] : (col == 1 ? oxs[1] : oxs[2]))) * a.wi;
+            const int32_t idj = __float_as_int(rj.w);
+            if (idj < a.n_owned) oj[k] = (t_o[r] + (col == 0 ? oxs[0] : (col == 1 ? oxs[1] : oxs[2]))) * a.wi;
+            if (HALFIDS) {
+              // upper bound of idj in the cell's ascending ids
+              int32_t lo = 0, hi = ni;
+              while (lo < hi) {
+                const int32_t mid = (lo + hi) >> 1;
+                if (__ldg(a.sorted_ids + ibeg + mid) <= idj)
+                  lo = mid + 1;
+                else
+                  hi = mid;
+              }
+              pj[k] = lo;
+            }
           }
         }
         f32x2 X[PM_RJ / 2], Y[PM_RJ / 2], Z[PM_RJ / 2], W[PM_RJ / 2];
@@ -824,6 +843,13 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
               }
             }
           }
+          if (HALFIDS) {
+#pragma unroll
+            for (int k = 0; k < PM_RJ; k++) {
+              const int32_t cut = pj[k] - w * 32;  // particles w*32 .. w*32 + cut - 1 have an id <= the candidate's
+              hits[k] = cut <= 0 ? hits[k] : (cut >= 32 ? 0u : (hits[k] & (0xffffffffu >> cut)));
+            }
+          }
 #pragma unroll
           for (int k = 0; k < PM_RJ; k++)
             if (oj[k] >= 0) a.mask[(long long)(oj[k] + w) * a.n_cap + sj[k]] = hits[k];
@@ -847,6 +873,7 @@ struct EmitArgs {
   int32_t mesh[3];
   int32_t n_total, n_owned;
   int32_t n_cells;  // cell_start[n_cells] = particles present (n_total minus absent ghosts) = slots in use
+  int32_t clear_self;  // 1: a row's own bit is set in the masks and has to be dropped (FULL lists)
   const uint32_t* mask;
   long long n_cap;
   int32_t wi;
@@ -914,7 +941,10 @@ __global__ void __launch_bounds__(128) rowcount_kernel(EmitArgs a) {
   const int32_t id = __ldg(a.sorted_ids + slot);
   if (id >= a.n_owned) return;
   int32_t cnt = 0;
-  walk_words<true>(a, slot, __ldg(a.slot_cell + slot), [&](uint32_t word, int32_t) { cnt += __popc(word); });
+  if (a.clear_self)
+    walk_words<true>(a, slot, __ldg(a.slot_cell + slot), [&](uint32_t word, int32_t) { cnt += __popc(word); });
+  else
+    walk_words<false>(a, slot, __ldg(a.slot_cell + slot), [&](uint32_t word, int32_t) { cnt += __popc(word); });
   a.counts[id] = cnt;
 }
 
@@ -1078,7 +1108,7 @@ __global__ void __launch_bounds__(EM_WARPS * 32) emit_kernel(EmitArgs a) {
         m[k][0] = nw[k] > 0 ? mp[oy][k][0] : 0u;
         m[k][1] = nw[k] > 1 ? mp[oy][k][1] : 0u;
       }
-      const bool own_run = !HALF && rv && (zlo + oz == bz) && (ylo + oy == by);  // FULL: j != i
+      const bool own_run = !HALF && a.clear_self && rv && (zlo + oz == bz) && (ylo + oy == by);  // FULL: j != i
       if (own_run) {
 #pragma unroll
         for (int k = 0; k < 3; k++)

@@ -524,12 +524,14 @@ def test_kernel_variants_emit_identical_lists(cuda, oracle, mode):
     from md_neighbor_list_b200 import workloads
     q = workloads.fcc(1.0, 23.0)
     box = (23.0, 23.0, 23.0)
-    outs = [gpu_build(cuda, q, 3.3, box, mode, kernel_variant=v) for v in (1, 2, 3)]
+    # 4 = HALF rows filtered by id during the emission (the multi-GPU path) instead of inside the masks
+    outs = [gpu_build(cuda, q, 3.3, box, mode, kernel_variant=v) for v in (1, 2, 3, 4)]
     for o in outs[1:]:
         assert o["pairs"] == outs[0]["pairs"]
         assert np.array_equal(o["np"], outs[0]["np"])
         assert np.array_equal(o["off"], outs[0]["off"])
     assert np.array_equal(outs[1]["list"], outs[2]["list"])
+    assert np.array_equal(outs[1]["list"], outs[3]["list"])
     if mode == "full_csr":
         assert np.array_equal(outs[0]["list"], outs[1]["list"])
     ref = oracle.build_full(q, 3.3, box) if mode == "full_csr" else oracle.build_half(q, 3.3, box)
