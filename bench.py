@@ -216,9 +216,14 @@ def run_ours(args):
     max_entries = 0 if halo is None else int(n_owned * 4.18879 * SL ** 3 * 1.3)
     nl.initialize(cap_particles, max_entries)
 
+    graphed = None  # set after the capacities have settled (below)
+
     def one_build(qd_local=None):
+        nonlocal_graphed = graphed
         if halo is None:
             nl.build(q_dev, stream=stream)
+        elif nonlocal_graphed is not None:
+            nonlocal_graphed.step()
         else:
             halo.build(nl, q_dev, stream, gid_owned=gid_dev)
 
@@ -244,6 +249,15 @@ def run_ours(args):
     with torch.cuda.stream(stream):
         one_build()
     sync_growing()
+    if halo is not None and os.environ.get("NLB_HALO_GRAPH", "0") == "1":
+        # opt-in experiment (measured at 2 GPUs: hot 0.234 ms vs 0.238 eager, cold 0.31 vs 0.25, and the process group
+        # was slow to shut down after NCCL ops had been captured): exchange + build of identical steps as ONE CUDA graph (packing kernels, NCCL group, the build's kernel chain);
+        # captured only now that no capacity will be reallocated
+        g = parallel.GraphedHaloBuild(halo, nl, q_dev, gid_dev, stream)
+        if g.graph is not None:
+            graphed = g
+        elif rank == 0:
+            print("halo graph capture refused, eager steps: " + getattr(g, "error", "?")[:300], file=sys.stderr)
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
             one_build()
@@ -416,7 +430,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world),
+            "config": dict(workload_config(world), **({"halo": "exchange + build replayed as one CUDA graph"}
+                                                      if graphed is not None else {})),
             "clocks": clocks,
             "e2e": {"value": pairs_all / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(q_pinned.numel() * 8),

@@ -145,6 +145,11 @@ int nlb200_build(nlb200_handle h, const void* q_dev, int64_t n, void* stream);
 int nlb200_build_subset(nlb200_handle h, const void* q_dev, int64_t n_total, int64_t n_owned,
                         const int32_t* global_ids_dev, void* stream);
 
+/* For callers that capture nlb200_build / nlb200_build_subset into a CUDA graph of their own (on a capturing stream the
+ * library enqueues its plain kernel chain instead of replaying its own graph) and replay it: tells the handle that the captured build was enqueued again on `stream`, so that
+ * nlb200_synchronize waits for it and fetches its status. */
+int nlb200_mark_enqueued(nlb200_handle h, void* stream);
+
 /* Replaces the `sync` argument / cudaDeviceSynchronize of neighlist_gpu.hpp:465 and make_list.cu:128: waits for the
  * last build on its stream, fetches the device status word and statistics.  Returns the build's status. */
 int nlb200_synchronize(nlb200_handle h);

@@ -39,6 +39,7 @@ SYMBOLS = {
     "nlb200_destroy": (C.c_int, [_vp]),
     "nlb200_build": (C.c_int, [_vp, _vp, _i64, _vp]),
     "nlb200_build_subset": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "nlb200_mark_enqueued": (C.c_int, [_vp, _vp]),
     "nlb200_synchronize": (C.c_int, [_vp]),
     "nlb200_build_host": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
     "nlb200_fetch_partners_host": (C.c_int, [_vp, _vp, _i64]),

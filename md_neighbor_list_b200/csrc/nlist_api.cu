@@ -728,6 +728,7 @@ int nlb200_build_subset(nlb200_handle h, const void* q_dev, int64_t n_total, int
     return fail(h, NLB200_ERR_INVALID, "particle count %lld (owned %lld) outside [0, %lld]", (long long)n_total,
                 (long long)n_owned, (long long)h->max_n);
   if (n_total > 0 && q_dev == nullptr) return fail(h, NLB200_ERR_INVALID, "null position pointer");
+  (void)cudaGetLastError();  // a non-sticky error left behind by another library must not be reported as ours
   const size_t align = (h->stride == 4) ? 16 : (h->dtype == NLB200_F64 ? 8 : 4);
   if ((reinterpret_cast<uintptr_t>(q_dev) % align) != 0)
     return fail(h, NLB200_ERR_INVALID, "position pointer must be %zu-byte aligned", align);
@@ -741,7 +742,13 @@ int nlb200_build_subset(nlb200_handle h, const void* q_dev, int64_t n_total, int
     CK(h, cudaMemsetAsync(h->ell_prev, 0, sizeof(int32_t) * (size_t)(h->max_n > 0 ? h->max_n : 1), s));
     h->ell_last_n = n_owned;
   }
-  const bool can_graph = h->use_graph && !h->profile && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
+  bool can_graph = h->use_graph && !h->profile && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
+  if (can_graph) {
+    // the caller is capturing this stream into a graph of its own (e.g. halo exchange + build as one graph): enqueue
+    // the plain kernel chain, which becomes part of that graph
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) can_graph = false;
+  }
   if (can_graph) {
     const bool hit = h->graph_exec && h->g_q == q_dev && h->g_n == n_total && h->g_owned == n_owned &&
                      h->g_gids == global_ids_dev;
@@ -782,6 +789,15 @@ int nlb200_build_subset(nlb200_handle h, const void* q_dev, int64_t n_total, int
   h->have_result = false;
   h->last_n = n_total;
   h->last_owned = n_owned;
+  return NLB200_OK;
+}
+
+int nlb200_mark_enqueued(nlb200_handle h, void* stream) {
+  if (!h) return NLB200_ERR_INVALID;
+  if (!h->initialized || h->last_n < 0) return fail(h, NLB200_ERR_STATE, "no build to mark");
+  h->last_stream = reinterpret_cast<cudaStream_t>(stream);
+  h->build_pending = true;
+  h->have_result = false;
   return NLB200_OK;
 }
 
@@ -936,6 +952,7 @@ const char* nlb200_last_error(nlb200_handle h) { return h ? h->err.c_str() : "nu
 
 int nlb200_track_reference(nlb200_handle h, const void* q_dev, int64_t n, void* stream) {
   if (!h) return NLB200_ERR_INVALID;
+  (void)cudaGetLastError();
   if (!h->initialized) return fail(h, NLB200_ERR_STATE, "track before initialize");
   if (n < 0 || n > h->max_n || (n > 0 && !q_dev)) return fail(h, NLB200_ERR_INVALID, "particle count out of range");
   const size_t esz = h->dtype == NLB200_F64 ? 8 : 4;
@@ -952,6 +969,7 @@ int nlb200_track_reference(nlb200_handle h, const void* q_dev, int64_t n, void* 
 
 int nlb200_max_displacement(nlb200_handle h, const void* q_dev, int64_t n, void* stream, double* max_disp_host) {
   if (!h || !max_disp_host) return NLB200_ERR_INVALID;
+  (void)cudaGetLastError();
   if (!h->q_ref) return fail(h, NLB200_ERR_STATE, "nlb200_max_displacement before nlb200_track_reference");
   if (n != h->q_ref_n) return fail(h, NLB200_ERR_INVALID, "particle count differs from the tracked reference");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -977,6 +995,7 @@ int nlb200_max_displacement(nlb200_handle h, const void* q_dev, int64_t n, void*
 int nlb200_lj_forces(nlb200_handle h, const void* q_dev, double rc, double epsilon, double sigma, double* forces_dev,
                      double* energy_dev, void* stream) {
   if (!h) return NLB200_ERR_INVALID;
+  (void)cudaGetLastError();
   if (!h->initialized || (!h->build_pending && !h->have_result))
     return fail(h, NLB200_ERR_STATE, "lj_forces needs a build");
   if (h->mode == NLB200_HALF_CSR) return fail(h, NLB200_ERR_INVALID, "lj_forces reads FULL rows");
@@ -998,6 +1017,7 @@ int nlb200_lj_forces(nlb200_handle h, const void* q_dev, double rc, double epsil
 
 int nlb200_gather_sorted(nlb200_handle h, const void* src_dev, int elem_bytes, int width, void* dst_dev, void* stream) {
   if (!h) return NLB200_ERR_INVALID;
+  (void)cudaGetLastError();
   if (!h->initialized || (!h->build_pending && !h->have_result))
     return fail(h, NLB200_ERR_STATE, "gather_sorted needs a build (the cell order comes from it)");
   if ((elem_bytes != 4 && elem_bytes != 8) || width < 1 || width > 16 || !src_dev || !dst_dev)
@@ -1094,6 +1114,7 @@ int nlb200_pack_slab2(const void* q_dev, const int32_t* gids_dev, int64_t n, int
                       int32_t* out_gid_hi_dev, int64_t capacity, int64_t* out_counts_dev, void* workspace_dev,
                       int64_t workspace_bytes, void* stream) {
   if (n < 0 || capacity < 0 || axis < 0 || axis > 2 || (stride != 3 && stride != 4)) return NLB200_ERR_INVALID;
+  (void)cudaGetLastError();  // a non-sticky error left behind by another library must not be reported as ours
   const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE + 1;
   // workspace: [flags_lo | pos_lo] [flags_hi | pos_hi] [scan state lo | scan state hi]
   const size_t o_pos = align_up(sizeof(int32_t) * (size_t)(n + 8), 256);
@@ -1130,7 +1151,13 @@ int nlb200_pack_slab2(const void* q_dev, const int32_t* gids_dev, int64_t n, int
     slab_pack2_kernel<float><<<gp, 256, 0, s>>>(
         (const float*)q_dev, gids_dev, flags[0], pos[0], flags[1], pos[1], n, stride, (float*)out_q_lo_dev,
         out_gid_lo_dev, (float*)out_q_hi_dev, out_gid_hi_dev, capacity, out_counts_dev);
-  return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    std::fprintf(stderr, "nlb200_pack_slab2: %s (n=%lld capacity=%lld)\n", cudaGetErrorString(e), (long long)n,
+                 (long long)capacity);
+    return NLB200_ERR_CUDA;
+  }
+  return NLB200_OK;
 }
 
 int64_t nlb200_select_slab_workspace(int64_t n) {

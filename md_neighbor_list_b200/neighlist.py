@@ -110,6 +110,10 @@ class VerletListB200:
             check(self._h, self._lib.nlb200_build_subset(self._h, q.data_ptr(), n, own, gid, s.cuda_stream))
             self.n = own
 
+    def _mark_pending(self, stream: torch.cuda.Stream) -> None:
+        """A build captured in an outer CUDA graph was replayed on `stream` (nlb200_mark_enqueued)."""
+        check(self._h, self._lib.nlb200_mark_enqueued(self._h, stream.cuda_stream))
+
     def synchronize(self) -> Stats:
         check(self._h, self._lib.nlb200_synchronize(self._h))
         return self.stats()

@@ -248,6 +248,38 @@ class SlabDecomposition:
         return None
 
 
+class GraphedHaloBuild:
+    """Exchange + build of identical steps (same buffers, same counts) replayed as ONE CUDA graph: the halo packing
+    kernels, the grouped NCCL send/recv and the build's kernel chain are captured once, so a
+    step costs one graph launch on the host instead of ~15 launches and a c10d group call.  For small systems the
+    host side is what limits a multi-GPU step.  Falls back to eager steps if the capture is refused."""
+
+    def __init__(self, halo: SlabDecomposition, nl, q_owned: torch.Tensor, gid_owned: torch.Tensor, stream):
+        self.halo, self.nl, self.q, self.g, self.stream = halo, nl, q_owned, gid_owned, stream
+        self.graph = None
+        for _ in range(3):  # allocations, communicators, the library's graph: all before the capture
+            halo.build(nl, q_owned, stream, gid_owned=gid_owned)
+        stream.synchronize()
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
+                halo.build(nl, q_owned, stream, gid_owned=gid_owned)
+            self.graph = g
+        except Exception as e:  # noqa: BLE001 — any capture problem means: stay eager
+            self.error = repr(e)
+            self.graph = None
+            torch.cuda.synchronize()
+
+    def step(self) -> None:
+        if self.graph is not None:
+            with torch.cuda.stream(self.stream):
+                self.graph.replay()
+            # the library must know that a build is in flight on this stream
+            self.nl._mark_pending(self.stream)
+        else:
+            self.halo.build(self.nl, self.q, self.stream, gid_owned=self.g)
+
+
 class _null:
     def __enter__(self):
         return self
