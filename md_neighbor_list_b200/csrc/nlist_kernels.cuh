@@ -527,25 +527,27 @@ __global__ void __launch_bounds__(128) search_kernel(SearchArgs<T> a) {
 // 5-7 (default path).  "pair masks": every distance test is evaluated ONCE per ordered pair, its verdict kept as one
 // bit, and the CSR rows are expanded from the bits after the offsets are known.
 //
-//   pairmask_kernel   CTA = cell A.  The particles i of A sit in shared memory ({x, y, z, (|x|^2 - SL^2)/2} in the
-//                     frame centred on A).  The candidates j — the <= 9 contiguous x-runs of A's stencil in the
-//                     cell-sorted array — are spread over the LANES, PM_RJ per lane in registers, translated once into
-//                     A's frame ({x, y, z, -|x|^2/2}).  Lane utilisation follows the ~950-long candidate list (>= 93 %)
-//                     instead of the ~35 particles of a cell (55 % of two warps), and one broadcast LDS.128 feeds
-//                     PM_RJ tests (the shared-memory return path bounded the thread-per-i form,
-//                     profiles/r01_microbench_issue_rates.txt).
-//                     Test, dot form:  d = xi.xj - |xj|^2/2 - (|xi|^2 - SL^2)/2 = (SL^2 - r^2)/2   (3 FFMA + 1 FADD);
-//                     its sign bit is funnel-shifted into the lane's 32-bit word (1 SHF), min|d| is tracked (FMNMX).
+//   pairmask_kernel   persistent warps draw (cell A, part) items from a queue.  The particles i of A sit in the warp's
+//                     shared memory, pre-duplicated for packed math ({xi,xi,yi,yi}, {zi,zi,-ai,-ai},
+//                     ai = (|xi|^2 - SL^2)/2, frame centred on A).  The candidates j — the <= 9 contiguous x-runs of A's
+//                     stencil in the cell-sorted array — are spread over the LANES, PM_RJ per lane in registers,
+//                     translated once into A's frame ({x, y, z, -|x|^2/2}).  Lane utilisation follows the ~950-long
+//                     candidate list (>= 93 %) instead of the ~35 particles of a cell (55 % of two warps), and two
+//                     broadcast LDS.128 feed PM_RJ tests (the shared-memory return path bounded the thread-per-i
+//                     form, profiles/r01_microbench_issue_rates.txt).
+//                     Test, dot form:  d = xi.xj - |xj|^2/2 - ai = (SL^2 - r^2)/2: 3 FFMA2 + 1 FADD2 per TWO tests;
+//                     the sign bit is funnel-shifted into the lane's 32-bit word (1 SHF), min|d| tracked (FMNMX3).
 //                     After 32 particles of A the lane holds, for ITS candidate j, the word "which i of A are within
 //                     SL of j" — by symmetry a piece of ROW j.  Only a word whose min|d| fell inside the uncertainty
-//                     band E is revisited with the exact input-precision test.
+//                     band E is revisited (by the whole warp, lane = particle) with the exact input-precision test.
 //                     mask[o][w][slot_j]: o = ordinal of A inside the stencil of j's cell, w = word (32 i's each).
-//   rowcount_kernel   thread = row: popcount (FULL) or id-filtered expansion (HALF) of the row's <= 27*WI words.
+//                     HALFIDS: the id filter of HALF lists is a suffix cut per (candidate, cell), see the kernel.
+//   rowcount_kernel   thread = row: popcount of the row's <= 27*WI words.
 //   scan_kernel       counts -> offsets (as before).
-//   emit_kernel       thread = row: expands set bits MSB-first (FLO) into a shared-memory staging area laid out as the
-//                     CTA's rows back to back; then warps copy each row to partners[offsets[id] ...] with coalesced
-//                     128-byte stores (scattered 4-byte stores cost more L2 sector writes than the whole test phase,
-//                     and at 16 M particles they turned into DRAM read-modify-writes).
+//   emit_kernel       thread = row: expands set bits MSB-first (FLO) into its line of a per-warp shared-memory tile;
+//                     when a line could overflow every lane flushes its own line to its row with 16-byte stores
+//                     (scattered 4-byte stores cost more L2 sector writes than the whole test phase, and at 16 M
+//                     particles they turned into DRAM read-modify-writes).
 //   Rows come out in stencil order: cells ascending, ids ascending inside a cell — the discovery order of the
 //   reference kernels (kernel_impl.cuh:17-33).
 // ---------------------------------------------------------------------------------------------------------------
