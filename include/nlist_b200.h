@@ -87,7 +87,11 @@ typedef enum {
   NLB200_OPT_PROFILE = 7,
   /* most particles one cell may hold — the reference's NMAX_IN_MESH (neighlist_gpu.hpp:74).  0 (default): estimated
    * from the mean occupancy at initialize (mean + 6 sigma).  Exceeding it is detected (NLB200_ERR_CELL_CAPACITY). */
-  NLB200_OPT_MAX_IN_CELL = 8
+  NLB200_OPT_MAX_IN_CELL = 8,
+  /* 1 (default): the kernels of a build are chained by programmatic dependent launch — a kernel's CTAs are scheduled
+   * while its predecessor drains and wait on the device for its results (no effect on the results).  0: plain
+   * stream order.  The environment variable NLB200_PDL=0/1 overrides the default at nlb200_create. */
+  NLB200_OPT_PDL = 9
 } nlb200_option;
 
 typedef struct {

@@ -54,6 +54,7 @@ struct nlb200_context {
   uint32_t* mask = nullptr;  // [27][mask_wi][mask_ncap] pair-mask words
   int32_t mask_wi = 0;       // words per (row, stencil cell): cells may hold up to 32*mask_wi particles
   int64_t mask_ncap = 0;
+  bool pdl = false;             // NLB200_OPT_PDL
   int64_t max_in_cell_opt = 0;  // NLB200_OPT_MAX_IN_CELL (0 = estimate from the density)
   int32_t* counts = nullptr;
   int64_t* offsets = nullptr;
@@ -195,11 +196,31 @@ void drop_graph(nlb200_context* h) {
   h->g_n = -1;
 }
 
+// ---- launches of the build chain --------------------------------------------------------------------------------
+// With programmatic dependent launch (NLB200_OPT_PDL, default on) a kernel's CTAs are scheduled while its predecessor
+// drains and block in pdl_enter() until the predecessor's writes are visible: the launch latency of the nine small
+// kernels of a build is hidden, inside a captured graph (programmatic edges) as well as on a plain stream.
+thread_local bool t_pdl = false;
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = t_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // ---- search-kernel dispatch -------------------------------------------------------------------------------------
 template <typename T, int STRIDE, bool HALF, bool FILL, bool EXACT>
 cudaError_t launch_search_t(const SearchArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
-  search_kernel<T, STRIDE, HALF, FILL, EXACT><<<grid, block, smem, s>>>(a);
-  return cudaGetLastError();
+  return launch_chain(search_kernel<T, STRIDE, HALF, FILL, EXACT>, dim3(grid), dim3(block), smem, s, a);
 }
 
 constexpr int MAX_SEARCH_SMEM = 200 * 1024;
@@ -225,14 +246,12 @@ constexpr int MAX_EMIT_SMEM = 200 * 1024;
 
 template <bool HALF, bool GID, bool COUNT>
 cudaError_t launch_emit_t(bool direct, const EmitArgs& a, cudaStream_t s) {
-  if (direct) {
-    emit_direct_kernel<HALF, GID, COUNT><<<(unsigned)((a.n_total + 127) / 128), 128, 0, s>>>(a);
-  } else {
-    constexpr int rows = EM_WARPS * 32;
-    emit_kernel<HALF, GID, COUNT><<<(unsigned)((a.n_total + rows - 1) / rows), rows,
-                                    (size_t)EM_WARPS * 32 * EM_LINE * sizeof(int32_t), s>>>(a);
-  }
-  return cudaGetLastError();
+  if (direct)
+    return launch_chain(emit_direct_kernel<HALF, GID, COUNT>, dim3((unsigned)((a.n_total + 127) / 128)), dim3(128), 0,
+                        s, a);
+  constexpr int rows = EM_WARPS * 32;
+  return launch_chain(emit_kernel<HALF, GID, COUNT>, dim3((unsigned)((a.n_total + rows - 1) / rows)), dim3(rows),
+                      (size_t)EM_WARPS * 32 * EM_LINE * sizeof(int32_t), s, a);
 }
 cudaError_t launch_emit(bool half, bool count, bool direct, const EmitArgs& a, cudaStream_t s) {
   const bool gid = a.global_ids != nullptr;
@@ -314,6 +333,7 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
   const int32_t n = (int32_t)n_total;
   const int32_t M = gp.n_cells;
   h->n_stages = 0;
+  t_pdl = h->pdl && !h->profile;  // stage events between the kernels would serialise them anyway
   auto stage = [&](int id) -> cudaError_t {
     if (!h->profile) return cudaSuccess;
     if (h->n_stages >= nlb200_context::MAX_STAGES) return cudaSuccess;
@@ -324,6 +344,7 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
   CK(h, cudaMemsetAsync(h->zero_region, 0, h->zero_bytes, s));
   CK(h, stage(ST_BIN));
   if (n > 0) {
+    // first kernel of the chain: a plain launch behind the memset
     bin_kernel<T, STRIDE><<<(n + 255) / 256, 256, 0, s>>>(q, n, (int32_t)n_owned, gp, h->cell_count, h->cell_rank,
                                                           h->status_dev);
     CK(h, cudaGetLastError());
@@ -331,21 +352,24 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
   CK(h, stage(ST_SCAN_CELLS));
   {
     const int tiles = (int)((M + SCAN_TILE - 1) / SCAN_TILE);
-    scan_kernel<int32_t><<<tiles, SCAN_THREADS, 0, s>>>(h->cell_count, M, h->cell_start, nullptr,
-                                                        h->scan_state_cells, nullptr, &h->status_dev->max_in_cell,
-                                                        0);
-    CK(h, cudaGetLastError());
+    const bool after_kernel = n > 0;  // n == 0: the scan follows the memset directly
+    const bool keep = t_pdl;
+    t_pdl = keep && after_kernel;
+    CK(h, launch_chain(scan_kernel<int32_t>, dim3(tiles), dim3(SCAN_THREADS), 0, s, (const int32_t*)h->cell_count,
+                       (int64_t)M, h->cell_start, (int32_t*)nullptr, h->scan_state_cells, (DeviceStatus*)nullptr,
+                       &h->status_dev->max_in_cell, 0ll));
+    t_pdl = keep;
   }
   CK(h, stage(ST_SCATTER));
   if (n > 0) {
-    scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->cell_rank, n, h->cell_start, h->perm);
-    CK(h, cudaGetLastError());
+    CK(h, launch_chain(scatter_kernel, dim3((n + 255) / 256), dim3(256), 0, s, (const int2*)h->cell_rank, n,
+                       (const int32_t*)h->cell_start, h->perm));
     CK(h, stage(ST_CELLSORT));
     int64_t cs_blocks = ((int64_t)M * 32 + 127) / 128;
     if (cs_blocks > (int64_t)h->sm_count * 64) cs_blocks = (int64_t)h->sm_count * 64;  // warps stride over the cells
-    cellsort_kernel<T, STRIDE><<<(unsigned)cs_blocks, 128, 0, s>>>(
-        q, gp, h->cell_start, h->perm, h->sorted_ids, h->rec, h->slot_cell, gids, h->slot_gid);
-    CK(h, cudaGetLastError());
+    CK(h, launch_chain(cellsort_kernel<T, STRIDE>, dim3((unsigned)cs_blocks), dim3(128), 0, s, q, gp,
+                       (const int32_t*)h->cell_start, (const int32_t*)h->perm, h->sorted_ids, h->rec, h->slot_cell,
+                       gids, h->slot_gid));
   }
   const bool half = h->mode == NLB200_HALF_CSR;
   const bool use_v1 = h->exact_only != 0 || h->variant == 1;
@@ -379,10 +403,9 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     CK(h, stage(ST_SCAN_COUNTS));
     {
       const int tiles = (int)((n_owned + SCAN_TILE - 1) / SCAN_TILE);
-      scan_kernel<int64_t><<<tiles > 0 ? tiles : 1, SCAN_THREADS, 0, s>>>(
-          h->counts, n_owned, h->offsets, h->offsets32, h->scan_state_counts, h->status_dev,
-          &h->status_dev->max_partners, (long long)h->cap_entries);
-      CK(h, cudaGetLastError());
+      CK(h, launch_chain(scan_kernel<int64_t>, dim3(tiles > 0 ? tiles : 1), dim3(SCAN_THREADS), 0, s,
+                         (const int32_t*)h->counts, (int64_t)n_owned, h->offsets, h->offsets32, h->scan_state_counts,
+                         h->status_dev, &h->status_dev->max_partners, (long long)h->cap_entries));
     }
     CK(h, stage(ST_FILL));
     if (n > 0) CK(h, (launch_search<T, STRIDE>(half, true, h->exact_only != 0, a, M, block, smem, s)));
@@ -452,43 +475,39 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
       const int64_t need = (M * parts + PM_THREADS / 32 - 1) / (PM_THREADS / 32);
       if (grid > need) grid = need;
       if (half_in_mask)
-        pairmask_kernel<T, STRIDE, true><<<(unsigned)grid, PM_THREADS, pm_smem, s>>>(pm);
+        CK(h, launch_chain(pairmask_kernel<T, STRIDE, true>, dim3((unsigned)grid), dim3(PM_THREADS), pm_smem, s, pm));
       else
-        pairmask_kernel<T, STRIDE, false><<<(unsigned)grid, PM_THREADS, pm_smem, s>>>(pm);
-      CK(h, cudaGetLastError());
+        CK(h, launch_chain(pairmask_kernel<T, STRIDE, false>, dim3((unsigned)grid), dim3(PM_THREADS), pm_smem, s, pm));
     }
     CK(h, stage(ST_ROWCOUNT));
     if (n > 0) {
       if (half_emit) {
         CK(h, launch_emit(true, true, direct, em, s));  // HALF rows need the ids to count
       } else {
-        rowcount_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(em);
-        CK(h, cudaGetLastError());
+        CK(h, launch_chain(rowcount_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, s, em));
       }
     }
     CK(h, stage(ST_SCAN_COUNTS));
     {
       const int tiles = (int)((n_owned + SCAN_TILE - 1) / SCAN_TILE);
-      scan_kernel<int64_t><<<tiles > 0 ? tiles : 1, SCAN_THREADS, 0, s>>>(
-          h->counts, n_owned, h->offsets, h->offsets32, h->scan_state_counts, h->status_dev,
-          &h->status_dev->max_partners, (long long)h->cap_entries);
-      CK(h, cudaGetLastError());
+      CK(h, launch_chain(scan_kernel<int64_t>, dim3(tiles > 0 ? tiles : 1), dim3(SCAN_THREADS), 0, s,
+                         (const int32_t*)h->counts, (int64_t)n_owned, h->offsets, h->offsets32, h->scan_state_counts,
+                         h->status_dev, &h->status_dev->max_partners, (long long)h->cap_entries));
     }
     CK(h, stage(ST_EMIT));
     if (n > 0) CK(h, launch_emit(half_emit, false, direct, em, s));
   }
   if (h->sort_rows) CK(h, stage(ST_SORT_ROWS));
   if (h->sort_rows && n_owned > 0) {
-    sort_rows_kernel<<<(unsigned)((n_owned + SORT_WARPS - 1) / SORT_WARPS), SORT_WARPS * 32, 0, s>>>(
-        h->offsets, (int32_t)n_owned, h->partners, (long long)h->cap_entries);
-    CK(h, cudaGetLastError());
+    CK(h, launch_chain(sort_rows_kernel, dim3((unsigned)((n_owned + SORT_WARPS - 1) / SORT_WARPS)),
+                       dim3(SORT_WARPS * 32), 0, s, (const int64_t*)h->offsets, (int32_t)n_owned, h->partners,
+                       (long long)h->cap_entries));
   }
   if (h->mode == NLB200_FULL_ELL_TRANSPOSED) CK(h, stage(ST_ELL));
   if (h->mode == NLB200_FULL_ELL_TRANSPOSED && n_owned > 0) {
-    ell_kernel<<<(unsigned)((n_owned + 255) / 256), 256, 0, s>>>(h->offsets, h->partners, (int32_t)n_owned,
-                                                                h->ell_rows, h->ell, h->ell_prev,
-                                                                (long long)h->cap_entries, h->status_dev);
-    CK(h, cudaGetLastError());
+    CK(h, launch_chain(ell_kernel, dim3((unsigned)((n_owned + 255) / 256)), dim3(256), 0, s,
+                       (const int64_t*)h->offsets, (const int32_t*)h->partners, (int32_t)n_owned, h->ell_rows, h->ell,
+                       h->ell_prev, (long long)h->cap_entries, h->status_dev));
   }
   CK(h, stage(ST_STATUS));
   CK(h, cudaMemcpyAsync(h->status_host, h->status_dev, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, s));
@@ -579,6 +598,7 @@ int nlb200_create(double search_length, double lx, double ly, double lz, int dty
   h->L[2] = lz;
   h->dtype = dtype;
   h->mode = mode;
+  if (const char* e = std::getenv("NLB200_PDL")) h->pdl = std::atoi(e) != 0;
   const bool ok = (dtype == NLB200_F64) ? make_grid<double>(search_length, h->L, &h->gp64)
                                         : make_grid<float>(search_length, h->L, &h->gp32);
   if (!ok) {
@@ -610,6 +630,7 @@ int nlb200_set_option(nlb200_handle h, int option, int64_t value) {
     case NLB200_OPT_USE_GRAPH: h->use_graph = value != 0; return NLB200_OK;
     case NLB200_OPT_KERNEL_VARIANT: h->variant = (int)value; return NLB200_OK;
     case NLB200_OPT_PROFILE: h->profile = value != 0; return NLB200_OK;
+    case NLB200_OPT_PDL: h->pdl = value != 0; return NLB200_OK;
     case NLB200_OPT_MAX_IN_CELL:
       if (value < 0 || value > (1 << 20)) return fail(h, NLB200_ERR_INVALID, "max particles per cell out of range");
       h->max_in_cell_opt = value;

@@ -70,6 +70,15 @@ struct GridParams {
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Programmatic dependent launch (PDL): every kernel of the build chain first lets its successor's CTAs be scheduled
+// (they occupy free slots only: the trigger fires once ALL CTAs of this grid have started) and then waits until its
+// predecessor has completed and its writes are visible.  The chain is transitive because no kernel passes the wait
+// before its own predecessor is done.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 template <typename T>
 struct Vec3 {
   T x, y, z;
@@ -128,6 +137,7 @@ template <typename T, int STRIDE>
 __global__ void __launch_bounds__(256) bin_kernel(const T* __restrict__ q, int32_t n, int32_t n_owned,
                                                   GridParams<T> gp, int32_t* __restrict__ cell_count,
                                                   int2* __restrict__ cell_rank, DeviceStatus* __restrict__ st) {
+  pdl_enter();
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Vec3<T> p = load_pos<T, STRIDE>(q, i);
@@ -176,6 +186,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int32_t* __res
                                                             unsigned long long* __restrict__ state,
                                                             DeviceStatus* __restrict__ st, int32_t* max_out,
                                                             long long capacity) {
+  pdl_enter();
   __shared__ long long warp_sums[SCAN_THREADS / 32];
   __shared__ long long tile_prefix_s;
   __shared__ int tile_s;
@@ -297,6 +308,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int32_t* __res
 __global__ void __launch_bounds__(256) scatter_kernel(const int2* __restrict__ cell_rank, int32_t n,
                                                       const int32_t* __restrict__ cell_start,
                                                       int32_t* __restrict__ perm) {
+  pdl_enter();
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int2 cr = cell_rank[i];
@@ -318,6 +330,7 @@ __global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, 
                                                        int32_t* __restrict__ slot_cell,
                                                        const int32_t* __restrict__ global_ids,
                                                        int32_t* __restrict__ slot_pid) {
+  pdl_enter();
   // warps stride over the cells (a slab rank bins on the global grid: most of its cells are empty)
   const int lane = lane_id();
   const int32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -391,6 +404,7 @@ __device__ __forceinline__ void axis_range(int c, int m, int& lo, int& hi) {
 
 template <typename T, int STRIDE, bool HALF, bool FILL, bool EXACT_ONLY>
 __global__ void __launch_bounds__(128) search_kernel(SearchArgs<T> a) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* sj = reinterpret_cast<float4*>(smem_raw);
   int32_t* sid = reinterpret_cast<int32_t*>(smem_raw + (size_t)a.jt * sizeof(float4));
@@ -628,6 +642,7 @@ __host__ __device__ inline size_t pm_warp_bytes(int wi) {
 // per test, the popcount pass and the emission then see HALF rows directly.
 template <typename T, int STRIDE, bool HALFIDS>
 __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairMaskArgs<T> a) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   unsigned char* wbase = smem_raw + (size_t)warp * pm_warp_bytes(a.wi);
@@ -731,25 +746,41 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
         int32_t sj[PM_RJ];  // candidate's slot
         int32_t oj[PM_RJ];  // its mask plane for this cell (o * wi); -1: tail lane or ghost row, nothing to store
         int32_t pj[PM_RJ];  // HALFIDS: particles of this cell with an id <= the candidate's (they are not kept)
-        int r = 0;
+        // three passes so that the PM_RJ record loads are in flight together: slots first (shared-memory look-ups
+        // only), then every load, then the translation — the run look-up loop between two loads used to serialise
+        // them into PM_RJ round trips per chunk
+        int32_t rcol[PM_RJ];  // run * 4 + column; -1: tail lane
+        {
+          int r = 0;
+#pragma unroll
+          for (int k = 0; k < PM_RJ; k++) {
+            const int32_t c = c0 + k * 32 + lane;
+            sj[k] = 0;
+            rcol[k] = -1;
+            if (c < nj) {
+              while (c >= t_pre[r + 1]) r++;
+              const int32_t s = t_start[r] + (c - t_pre[r]);
+              sj[k] = s;
+              rcol[k] = r * 4 + ((s >= t_b1[r]) ? 1 : 0) + ((s >= t_b2[r]) ? 1 : 0);
+            }
+          }
+        }
+        float4 rjv[PM_RJ];
+#pragma unroll
+        for (int k = 0; k < PM_RJ; k++) rjv[k] = __ldg(a.rec + sj[k]);  // tail lanes read slot 0 (present: ni > 0)
 #pragma unroll
         for (int k = 0; k < PM_RJ; k++) {
-          const int32_t c = c0 + k * 32 + lane;
           xj[k] = yj[k] = zj[k] = 0.f;
           wj[k] = -1.0e30f;  // d = -1e30: a miss, far from the band
-          sj[k] = 0;
           oj[k] = -1;
           pj[k] = 0;
-          if (c < nj) {
-            while (c >= t_pre[r + 1]) r++;
-            const int32_t s = t_start[r] + (c - t_pre[r]);
-            const int32_t col = ((s >= t_b1[r]) ? 1 : 0) + ((s >= t_b2[r]) ? 1 : 0);
-            const float4 rj = __ldg(a.rec + s);
+          if (rcol[k] >= 0) {
+            const int r = rcol[k] >> 2, col = rcol[k] & 3;
+            const float4 rj = rjv[k];
             xj[k] = fmaf(tx0 + (float)col, msx, rj.x);
             yj[k] = fmaf(t_ty[r], msy, rj.y);
             zj[k] = fmaf(t_tz[r], msz, rj.z);
             wj[k] = -0.5f * fmaf(xj[k], xj[k], fmaf(yj[k], yj[k], zj[k] * zj[k]));
-            sj[k] = s;
             // rec.w carries the particle's local id (cellsort_kernel): rows of ghosts (id >= n_owned) are not stored
             const int32_t idj = __float_as_int(rj.w);
             if (idj < a.n_owned) oj[k] = (t_o[r] + (col == 0 ? oxs[0] : (col == 1 ? oxs[1] : oxs[2]))) * a.wi;
@@ -936,17 +967,65 @@ __device__ __forceinline__ void walk_words(const EmitArgs& a, int32_t slot, int3
     }
 }
 
-// FULL lists: the row length is a popcount of the row's mask words (without its own bit).
+// FULL lists: the row length is a popcount of the row's mask words (without its own bit).  Thread = row.  All loads
+// of a stencil plane (12 cell starts + 18 words) are issued before any is used and the word loads do not wait for the
+// cell starts — the kernel is bound by load latency, not by the 26 MB it reads from L2 (walk_words, one x-run at a
+// time with the words behind the cell starts, took 9 x 2 dependent round trips per row: 14 us vs this form's 3).
 __global__ void __launch_bounds__(128) rowcount_kernel(EmitArgs a) {
+  pdl_enter();
   const int32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= a.n_total || slot >= __ldg(a.cell_start + a.n_cells)) return;
   const int32_t id = __ldg(a.sorted_ids + slot);
   if (id >= a.n_owned) return;
+  const int32_t cell = __ldg(a.slot_cell + slot);
+  const int32_t mx = a.mesh[0], my = a.mesh[1], mz = a.mesh[2];
+  const int32_t bx = cell % mx, by = (cell / mx) % my, bz = cell / (mx * my);
+  int xlo, xhi, ylo, yhi, zlo, zhi;
+  axis_range(bx, mx, xlo, xhi);
+  axis_range(by, my, ylo, yhi);
+  axis_range(bz, mz, zlo, zhi);
+  const int32_t nx = xhi - xlo + 1, ny = yhi - ylo + 1, nz = zhi - zlo + 1;
+  const uint32_t* mrow = a.mask + slot;
+  const bool two = a.wi >= 2;
   int32_t cnt = 0;
-  if (a.clear_self)
-    walk_words<true>(a, slot, __ldg(a.slot_cell + slot), [&](uint32_t word, int32_t) { cnt += __popc(word); });
-  else
-    walk_words<false>(a, slot, __ldg(a.slot_cell + slot), [&](uint32_t word, int32_t) { cnt += __popc(word); });
+  for (int oz = 0; oz < nz; oz++) {
+    int32_t cbp[3][4];
+    uint32_t mp[3][3][2];
+#pragma unroll
+    for (int oy = 0; oy < 3; oy++) {
+      const bool rv = oy < ny;
+      const int32_t* cs = a.cell_start + ((ylo + oy) + (zlo + oz) * my) * mx + xlo;
+#pragma unroll
+      for (int k = 0; k < 4; k++) cbp[oy][k] = (rv && k <= nx) ? __ldg(cs + k) : 0;
+      const int32_t o0 = (oz * 3 + oy) * 3 * a.wi;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const bool cv = rv && k < nx;
+        mp[oy][k][0] = cv ? __ldg(mrow + (long long)(o0 + k * a.wi) * a.n_cap) : 0u;
+        mp[oy][k][1] = (cv && two) ? __ldg(mrow + (long long)(o0 + k * a.wi + 1) * a.n_cap) : 0u;
+      }
+    }
+#pragma unroll
+    for (int oy = 0; oy < 3; oy++) {
+      const int32_t o0 = (oz * 3 + oy) * 3 * a.wi;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int32_t nw = (oy < ny && k < nx) ? min((cbp[oy][k + 1] - cbp[oy][k] + 31) >> 5, a.wi) : 0;
+        if (nw > 0) cnt += __popc(mp[oy][k][0]);
+        if (nw > 1) cnt += __popc(mp[oy][k][1]);
+        for (int32_t w = 2; w < nw; w++) cnt += __popc(__ldg(mrow + (long long)(o0 + k * a.wi + w) * a.n_cap));
+      }
+    }
+  }
+  if (a.clear_self) {
+    // the row's own bit (r2 = 0 passes the test unless the record is NaN): FULL rows hold j != i (kernel_impl.cuh:29)
+    const int32_t own = slot - __ldg(a.cell_start + cell);
+    if ((own >> 5) < a.wi) {
+      const int32_t o = ((bz - zlo) * 3 + (by - ylo)) * 3 + (bx - xlo);
+      const uint32_t word = __ldg(mrow + (long long)(o * a.wi + (own >> 5)) * a.n_cap);
+      cnt -= (int32_t)((word >> (31 - (own & 31))) & 1u);
+    }
+  }
   a.counts[id] = cnt;
 }
 
@@ -955,6 +1034,7 @@ __global__ void __launch_bounds__(128) rowcount_kernel(EmitArgs a) {
 // 144 us vs 101 us staged on the default system, 5.9 ms vs 1.7 ms at 2 M uniform particles.
 template <bool HALF, bool GID, bool COUNT>
 __global__ void __launch_bounds__(128) emit_direct_kernel(EmitArgs a) {
+  pdl_enter();
   if (!COUNT) {
     if (a.offsets[a.n_owned] > a.capacity) return;
   }
@@ -987,6 +1067,9 @@ __global__ void __launch_bounds__(128) emit_direct_kernel(EmitArgs a) {
 //   slots are turned into partner ids (gather from sorted_ids / global_ids) and stored with coalesced 128-byte
 //   stores at partners[offsets[id] + done ...].  4 KB of tile per warp instead of whole rows keeps ~24 warps per SM
 //   resident; the expansion is a chain of dependent ALU/XU ops and needs that many to hide its latency.
+// Rejected (measured): one warp per (32 rows, stencil plane) — three times the warps, a third of the serial chain per
+// lane — emits the default system in 77.7 us vs 75.9 us: the kernel is not short of parallelism, its issue slots, XU
+// (FLO) and LSU wavefronts are each ~40-50 % busy.
 // HALF:  rows keep the partners with a larger (global) id (neighlist_cpu.hpp:225-236); the filter runs in the flush
 //        (ballot compaction).  COUNT: write counts[id] instead of partners (HALF lists need the ids to count).
 #ifndef NLB_EM_WARPS
@@ -998,9 +1081,13 @@ constexpr int EM_WARPS = NLB_EM_WARPS;
 #endif
 constexpr int EM_TILE = NLB_EM_TILE;
 constexpr int EM_LINE = EM_TILE + 1;  // +1: lanes with equal fill hit different banks
+#ifndef NLB_EM_MINB
+#define NLB_EM_MINB 14
+#endif
 
 template <bool HALF, bool GID, bool COUNT>
-__global__ void __launch_bounds__(EM_WARPS * 32) emit_kernel(EmitArgs a) {
+__global__ void __launch_bounds__(EM_WARPS * 32, NLB_EM_MINB) emit_kernel(EmitArgs a) {
+  pdl_enter();
   extern __shared__ __align__(16) int32_t em_smem[];
   if (!COUNT) {
     if (a.offsets[a.n_owned] > a.capacity) return;  // overflow already flagged by the offsets scan
@@ -1215,6 +1302,7 @@ __device__ __forceinline__ void bitonic_warp(int32_t* buf, int len, int lane) {
 __global__ void __launch_bounds__(SORT_WARPS * 32) sort_rows_kernel(const int64_t* __restrict__ offsets,
                                                                     int32_t n_rows, int32_t* partners,
                                                                     long long capacity) {
+  pdl_enter();
   __shared__ int32_t sbuf[SORT_WARPS][SORT_SMEM];
   if (offsets[n_rows] > capacity) return;
   const int lane = lane_id();
@@ -1245,6 +1333,7 @@ __global__ void __launch_bounds__(256) ell_kernel(const int64_t* __restrict__ of
                                                   const int32_t* __restrict__ partners, int32_t n, int32_t rows,
                                                   int32_t* __restrict__ ell, int32_t* __restrict__ prev_count,
                                                   long long capacity, DeviceStatus* st) {
+  pdl_enter();
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (offsets[n] > capacity) return;
