@@ -1222,11 +1222,12 @@ __global__ void __launch_bounds__(EM_WARPS * 32, NLB_EM_MINB) emit_kernel(EmitAr
 #pragma unroll
           for (int u = 0; u < 2; u++) {
             uint32_t word = m[k][u];
-            const int32_t first = cb[k] + 32 * u;
+            const int32_t last = cb[k] + 32 * u + 31;  // slot of bit 0
             while (word) {
-              const int b = __clz(word);
-              word &= ~(0x80000000u >> b);
-              asm volatile("st.shared.s32 [%0], %1;" ::"r"(wa), "r"(first + b) : "memory");
+              uint32_t p;  // position of the highest set bit: one FLO, no 31 - clz
+              asm("bfind.u32 %0, %1;" : "=r"(p) : "r"(word));
+              word ^= 1u << p;
+              asm volatile("st.shared.s32 [%0], %1;" ::"r"(wa), "r"(last - (int32_t)p) : "memory");
               wa += 4u;
             }
           }

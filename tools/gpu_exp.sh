@@ -1,7 +1,7 @@
 # one experiment round on the GPU box: parity smoke, then the default-system bench per library variant, kernel variant
 # and PDL setting
 set -u
-timeout 600 bash tools/gpu_quick.sh 2>&1 | tail -4
+timeout 150 bash tools/gpu_quick.sh 2>&1 | tail -4
 cp md_neighbor_list_b200/lib/libnlist_b200.so /tmp/base.so
 for v in base $(ls md_neighbor_list_b200/lib/variants/ 2>/dev/null); do
   if [ "$v" != "base" ]; then cp md_neighbor_list_b200/lib/variants/$v md_neighbor_list_b200/lib/libnlist_b200.so; fi
