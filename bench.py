@@ -258,8 +258,14 @@ def run_ours(args):
             graphed = g
         elif rank == 0:
             print("halo graph capture refused, eager steps: " + getattr(g, "error", "?")[:300], file=sys.stderr)
+    # the clock sampler starts before the warm-up steps so that nothing idles the GPU between them and the timed region;
+    # warm-up steps are shaped like timed ones (L2 flush + build)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
+            flush_l2()
             one_build()
     st = nl.synchronize()
     if halo is not None:
@@ -273,9 +279,6 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- timed region: K builds, device-timed, L2 flushed before each ----
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t0 = time.time()
