@@ -422,6 +422,7 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     pm.mask = h->mask;
     pm.n_cap = h->mask_ncap;
     pm.wi = h->mask_wi;
+    pm.fits32 = (27ll * h->mask_wi * h->mask_ncap) < (1ll << 32) ? 1 : 0;
     pm.band = gp.band;
     pm.st = h->status_dev;
     EmitArgs em;

@@ -615,6 +615,7 @@ struct PairMaskArgs {
   uint32_t* mask;      // [27][wi][n_cap]
   long long n_cap;
   int32_t wi;
+  int32_t fits32;  // 27 * wi * n_cap < 2^32: mask element indices fit 32 bits
   float band;
   unsigned long long* queue;  // item counter (zeroed per build): warps draw (cell, part) items from it
   int32_t parts;   // items per cell: part p takes the candidate chunks p, p + parts, ...  (small systems: more
@@ -624,7 +625,10 @@ struct PairMaskArgs {
 };
 
 // per-warp shared memory: the cell's particles + its run table
-constexpr int PM_TAB = 64;  // ints: start[9] b1[9] b2[9] pre[10] o[9] ty[9] tz[9]
+// per-warp run table: int start[9] b1[9] b2[9] pre[10] (padded to 40 ints), then 27 float4 entries, one per (run, x column)
+// of the stencil: {tx, ty, tz} = translation of that cell into A's frame in cell units, .w = mask plane of A in the
+// stencil of that cell (o * wi, as int bits)
+constexpr int PM_TAB = 40 + 27 * 4;
 // particles are stored pre-duplicated for the packed FMAs: {xi, xi, yi, yi}, {zi, zi, -ai, -ai}; at most PM_WC words
 // (256 particles) of a cell are staged at a time, denser cells are walked in several rounds
 constexpr int PM_WC = 8;
@@ -651,14 +655,13 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
   int32_t* t_b1 = t_start + 9;
   int32_t* t_b2 = t_b1 + 9;
   int32_t* t_pre = t_b2 + 9;  // [10]
-  int32_t* t_o = t_pre + 10;
-  float* t_ty = reinterpret_cast<float*>(t_o + 9);
-  float* t_tz = t_ty + 9;
+  float4* t_rc = reinterpret_cast<float4*>(t_start + 40);  // [27], index run * 3 + column
 
   const GridParams<T>& gp = a.gp;
   const int32_t mx = gp.mesh[0], my = gp.mesh[1], mz = gp.mesh[2];
   const float msx = gp.msf[0], msy = gp.msf[1], msz = gp.msf[2];
   const float hx = 0.5f * msx, hy = 0.5f * msy, hz = 0.5f * msz;
+  const uint32_t ncap32 = (uint32_t)a.n_cap;
   unsigned long long band_local = 0, cand_local = 0;
 
   const long long n_items = (long long)gp.n_cells * a.parts;
@@ -714,21 +717,22 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
           t_start[lane] = s0;
           t_b1[lane] = b1;
           t_b2[lane] = b2;
-          t_o[lane] = o;
-          t_ty[lane] = ty;
-          t_tz[lane] = tz;
         }
         if (lane < 10) t_pre[lane] = incl - len;  // lane 9: len = 0 -> the total
+        // lane e = run * 3 + column writes that stencil cell's entry: everything a candidate's set-up needs from its
+        // cell comes from ONE 16-byte shared-memory load instead of six look-ups and the selects between them
+        const int er = lane / 3, ecol = lane - er * 3;
+        const float ty_e = __shfl_sync(0xffffffffu, ty, er & 15), tz_e = __shfl_sync(0xffffffffu, tz, er & 15);
+        const int32_t o_e = __shfl_sync(0xffffffffu, o, er & 15);
+        if (lane < 27) {
+          // ordinal (x part) of A inside the stencil of a candidate in column xlo + ecol
+          const int32_t ox = cx - axis_lo(min(xlo + ecol, mx - 1), mx);
+          t_rc[lane] = make_float4((float)(xlo + ecol - cx) - 0.5f, ty_e, tz_e, __int_as_float((o_e + ox) * a.wi));
+        }
       }
       __syncwarp();
       const int32_t nj = t_pre[9];
       if (lane == 0 && part == 0) cand_local += (unsigned long long)ni * (unsigned long long)nj;
-      const float tx0 = (float)(xlo - cx) - 0.5f;
-
-      // ordinal (x part) of this cell inside the stencil of a candidate in column xlo + col
-      int32_t oxs[3];
-#pragma unroll
-      for (int col = 0; col < 3; col++) oxs[col] = cx - axis_lo(min(xlo + col, mx - 1), mx);
 
       for (int32_t iw0 = 0; iw0 * 32 < ni; iw0 += PM_WC) {  // one round for cells of up to 256 particles
       const int32_t iw1 = min(iw0 + PM_WC, (ni + 31) >> 5);
@@ -749,7 +753,7 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
         // three passes so that the PM_RJ record loads are in flight together: slots first (shared-memory look-ups
         // only), then every load, then the translation — the run look-up loop between two loads used to serialise
         // them into PM_RJ round trips per chunk
-        int32_t rcol[PM_RJ];  // run * 4 + column; -1: tail lane
+        int32_t rcol[PM_RJ];  // run * 3 + column; -1: tail lane
         {
           int r = 0;
 #pragma unroll
@@ -761,7 +765,7 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
               while (c >= t_pre[r + 1]) r++;
               const int32_t s = t_start[r] + (c - t_pre[r]);
               sj[k] = s;
-              rcol[k] = r * 4 + ((s >= t_b1[r]) ? 1 : 0) + ((s >= t_b2[r]) ? 1 : 0);
+              rcol[k] = r * 3 + ((s >= t_b1[r]) ? 1 : 0) + ((s >= t_b2[r]) ? 1 : 0);
             }
           }
         }
@@ -775,15 +779,15 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
           oj[k] = -1;
           pj[k] = 0;
           if (rcol[k] >= 0) {
-            const int r = rcol[k] >> 2, col = rcol[k] & 3;
             const float4 rj = rjv[k];
-            xj[k] = fmaf(tx0 + (float)col, msx, rj.x);
-            yj[k] = fmaf(t_ty[r], msy, rj.y);
-            zj[k] = fmaf(t_tz[r], msz, rj.z);
+            const float4 tr = t_rc[rcol[k]];
+            xj[k] = fmaf(tr.x, msx, rj.x);
+            yj[k] = fmaf(tr.y, msy, rj.y);
+            zj[k] = fmaf(tr.z, msz, rj.z);
             wj[k] = -0.5f * fmaf(xj[k], xj[k], fmaf(yj[k], yj[k], zj[k] * zj[k]));
             // rec.w carries the particle's local id (cellsort_kernel): rows of ghosts (id >= n_owned) are not stored
             const int32_t idj = __float_as_int(rj.w);
-            if (idj < a.n_owned) oj[k] = (t_o[r] + (col == 0 ? oxs[0] : (col == 1 ? oxs[1] : oxs[2]))) * a.wi;
+            if (idj < a.n_owned) oj[k] = __float_as_int(tr.w);
             if (HALFIDS) {
               // upper bound of idj in the cell's ascending ids
               int32_t lo = 0, hi = ni;
@@ -883,9 +887,18 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
               hits[k] = cut <= 0 ? hits[k] : (cut >= 32 ? 0u : (hits[k] & (0xffffffffu >> cut)));
             }
           }
+          // element index (plane * n_cap + slot): one 32 x 32 -> 64-bit multiply-add (n_cap < 2^31), or plain 32-bit
+          // arithmetic when the whole mask has fewer than 2^32 words
+          if (a.fits32) {
 #pragma unroll
-          for (int k = 0; k < PM_RJ; k++)
-            if (oj[k] >= 0) a.mask[(long long)(oj[k] + w) * a.n_cap + sj[k]] = hits[k];
+            for (int k = 0; k < PM_RJ; k++)
+              if (oj[k] >= 0) a.mask[(uint32_t)(oj[k] + w) * ncap32 + (uint32_t)sj[k]] = hits[k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < PM_RJ; k++)
+              if (oj[k] >= 0)
+                a.mask[(unsigned long long)(uint32_t)(oj[k] + w) * ncap32 + (uint32_t)sj[k]] = hits[k];
+          }
         }
       }
       }
@@ -1205,20 +1218,20 @@ __global__ void __launch_bounds__(EM_WARPS * 32, NLB_EM_MINB) emit_kernel(EmitAr
           for (int u = 0; u < 2; u++)
             if (xlo + k == bx && (own >> 5) == u) m[k][u] &= ~(0x80000000u >> (own & 31));
       }
-      int32_t run_hits = 0;
+      int32_t cell_hits[3];
 #pragma unroll
-      for (int k = 0; k < 3; k++)
-#pragma unroll
-        for (int u = 0; u < 2; u++) run_hits += __popc(m[k][u]);
-      const bool slow_lane = max(nw[0], max(nw[1], nw[2])) > 2 || run_hits > EM_TILE - 3;
-      if (__any_sync(0xffffffffu, fill + run_hits > EM_TILE)) flush(false);  // leaves fill <= 3
+      for (int k = 0; k < 3; k++) cell_hits[k] = __popc(m[k][0]) + __popc(m[k][1]);
+      const bool slow_lane = max(nw[0], max(nw[1], nw[2])) > 2 ||
+                             max(cell_hits[0], max(cell_hits[1], cell_hits[2])) > EM_TILE - 3;
       if (!__any_sync(0xffffffffu, slow_lane)) {
         // stencil order: cell 0 (words 0, 1), cell 1, cell 2; lanes of a warp sit in the same or adjacent cells, so
-        // their popcounts of one word are alike and the per-word loops stay reasonably full
-        uint32_t wa = line_sa + 4u * (uint32_t)fill;  // shared-memory byte address of the next free entry
-        fill += run_hits;
+        // their popcounts of one word are alike and the per-word loops stay reasonably full.  The flush check runs
+        // per cell: the central run of a row holds up to ~65 partners, more than a line, but no single cell does.
 #pragma unroll
         for (int k = 0; k < 3; k++) {
+          if (__any_sync(0xffffffffu, fill + cell_hits[k] > EM_TILE)) flush(false);  // leaves fill <= 3
+          uint32_t wa = line_sa + 4u * (uint32_t)fill;  // shared-memory byte address of the next free entry
+          fill += cell_hits[k];
 #pragma unroll
           for (int u = 0; u < 2; u++) {
             uint32_t word = m[k][u];
@@ -1233,7 +1246,7 @@ __global__ void __launch_bounds__(EM_WARPS * 32, NLB_EM_MINB) emit_kernel(EmitAr
           }
         }
       } else {
-        // a cell of this run holds more than 64 particles (or the run alone overflows a line): word by word,
+        // a cell of this run holds more than 64 particles (or one cell alone overflows a line): word by word,
         // warp-uniform loop bounds, a flush check before every word
         for (int k = 0; k < 3; k++)
           for (int32_t w = 0; w < a.wi; w++) {
