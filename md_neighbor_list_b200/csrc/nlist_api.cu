@@ -473,6 +473,10 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
       if (grab < 1) grab = 1;
       if (grab > 64) grab = 64;
       pm.grab = (int32_t)grab;
+      if (M * parts >= (1ll << 31)) return fail(h, NLB200_ERR_INVALID, "cells x parts exceeds 2^31 items");
+      pm.d_parts = make_fastdiv((uint32_t)parts);
+      pm.d_mx = make_fastdiv((uint32_t)gp.mesh[0]);
+      pm.d_my = make_fastdiv((uint32_t)gp.mesh[1]);
       const int64_t need = (M * parts + PM_THREADS / 32 - 1) / (PM_THREADS / 32);
       if (grid > need) grid = need;
       if (half_in_mask)

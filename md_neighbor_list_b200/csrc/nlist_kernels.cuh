@@ -70,6 +70,30 @@ struct GridParams {
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Division by a run-time invariant (mesh extents, items per cell) as multiply-high + shift — a hardware integer
+// division is ~20 instructions and the per-item set-up of the pair-mask kernel did seven of them.  Exact for
+// 0 <= n < 2^31 (the round-up method; same construction as CUTLASS's FastDivmod).
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  f.mul = 0;
+  f.shr = 0;
+  if (d > 1) {
+    uint32_t lg = 0;
+    while ((1ull << lg) < d) lg++;  // ceil(log2 d)
+    const uint32_t p = 31 + lg;
+    f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+    f.shr = p - 32;
+  }
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  return f.d > 1 ? (__umulhi(n, f.mul) >> f.shr) : n;
+}
+
 // Programmatic dependent launch (PDL): every kernel of the build chain first lets its successor's CTAs be scheduled
 // (they occupy free slots only: the trigger fires once ALL CTAs of this grid have started) and then waits until its
 // predecessor has completed and its writes are visible.  The chain is transitive because no kernel passes the wait
@@ -616,6 +640,7 @@ struct PairMaskArgs {
   long long n_cap;
   int32_t wi;
   int32_t fits32;  // 27 * wi * n_cap < 2^32: mask element indices fit 32 bits
+  FastDiv d_parts, d_mx, d_my;  // item -> (cell, part), cell -> (cx, cy, cz)
   float band;
   unsigned long long* queue;  // item counter (zeroed per build): warps draw (cell, part) items from it
   int32_t parts;   // items per cell: part p takes the candidate chunks p, p + parts, ...  (small systems: more
@@ -674,7 +699,8 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
     long long next = 0;
     if (lane == 0) next = first_dyn + (long long)atomicAdd(a.queue, (unsigned long long)a.grab);  // in flight meanwhile
     for (long long item = base; item < base + a.grab && item < n_items; item++) {
-    const int32_t cell = (int32_t)(item / a.parts), part = (int32_t)(item - (long long)cell * a.parts);
+    // n_items < 2^31 (checked on the host): 32-bit fast division
+    const int32_t cell = (int32_t)fdiv((uint32_t)item, a.d_parts), part = (int32_t)item - cell * a.parts;
     const int32_t ibeg = __ldg(a.cell_start + cell);
     int32_t ni = __ldg(a.cell_start + cell + 1) - ibeg;
     if (ni > 0) {
@@ -682,21 +708,28 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
         if (lane == 0 && part == 0) atomicOr(&a.st->flags, FLAG_CELL_WORDS);  // the build fails; stay in range
         ni = 32 * a.wi;
       }
-      const int32_t cx = cell % mx;
-      const int32_t cy = (cell / mx) % my;
-      const int32_t cz = cell / (mx * my);
+      const int32_t cyz = (int32_t)fdiv((uint32_t)cell, a.d_mx);
+      const int32_t cx = cell - cyz * mx;
+      const int32_t cz = (int32_t)fdiv((uint32_t)cyz, a.d_my);
+      const int32_t cy = cyz - cz * my;
       int xlo, xhi, ylo, yhi, zlo, zhi;
       axis_range(cx, mx, xlo, xhi);
       axis_range(cy, my, ylo, yhi);
       axis_range(cz, mz, zlo, zhi);
       const int32_t ny = yhi - ylo + 1, nruns = ny * (zhi - zlo + 1);
       __syncwarp();  // the previous cell's readers are done
+      // the first two words of the cell's own particles are requested now, next to the run table's cell starts: one
+      // round trip instead of two before the first candidate can be set up
+      float4 pre_i[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) pre_i[u] = __ldg(a.rec + ibeg + min(u * 32 + lane, ni - 1));
       {
         // run table: lane r describes run r = (z, y); prefix of the run lengths by warp scan
         int32_t len = 0, s0 = 0, b1 = 0x7fffffff, b2 = 0x7fffffff, o = 0;
         float ty = 0.f, tz = 0.f;
         if (lane < nruns) {
-          const int z = zlo + lane / ny, y = ylo + lane % ny;
+          const int lz = ny == 3 ? (lane * 11) >> 5 : (ny == 2 ? lane >> 1 : lane);  // lane / ny for lane < 9
+          const int z = zlo + lz, y = ylo + lane - lz * ny;
           const int32_t* cs = a.cell_start + (y + z * my) * mx;
           s0 = __ldg(cs + xlo);
           if (xlo + 1 <= xhi) b1 = __ldg(cs + xlo + 1);
@@ -738,7 +771,7 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
       const int32_t iw1 = min(iw0 + PM_WC, (ni + 31) >> 5);
       if (iw0 > 0) __syncwarp();  // the previous round's readers are done
       for (int32_t k = iw0 * 32 + lane; k < min(ni, iw1 * 32); k += 32) {
-        const float4 r = __ldg(a.rec + ibeg + k);
+        const float4 r = k < 32 ? pre_i[0] : (k < 64 ? pre_i[1] : __ldg(a.rec + ibeg + k));
         const float x = r.x - hx, y = r.y - hy, z = r.z - hz;
         const float nai = -0.5f * (fmaf(x, x, fmaf(y, y, z * z)) - gp.sl2f);
         si[2 * (k - iw0 * 32)] = make_float4(x, x, y, y);
