@@ -650,10 +650,11 @@ struct PairMaskArgs {
 };
 
 // per-warp shared memory: the cell's particles + its run table
-// per-warp run table: int start[9] b1[9] b2[9] pre[10] (padded to 40 ints), then 27 float4 entries, one per (run, x column)
-// of the stencil: {tx, ty, tz} = translation of that cell into A's frame in cell units, .w = mask plane of A in the
-// stencil of that cell (o * wi, as int bits)
-constexpr int PM_TAB = 40 + 27 * 4;
+// per-warp run table: 9 int4 entries, one per x-run of the stencil, {end of the run in the candidate list, first slot
+// minus start in the candidate list, first slot of the 2nd cell, first slot of the 3rd cell}; then 27 float4 entries,
+// one per (run, x column): {tx, ty, tz} = translation of that cell into A's frame in cell units, .w = mask plane of A
+// in the stencil of that cell (o * wi, as int bits)
+constexpr int PM_TAB = 9 * 4 + 27 * 4;
 // particles are stored pre-duplicated for the packed FMAs: {xi, xi, yi, yi}, {zi, zi, -ai, -ai}; at most PM_WC words
 // (256 particles) of a cell are staged at a time, denser cells are walked in several rounds
 constexpr int PM_WC = 8;
@@ -676,11 +677,8 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   unsigned char* wbase = smem_raw + (size_t)warp * pm_warp_bytes(a.wi);
   float4* si = reinterpret_cast<float4*>(wbase);  // [32 * min(wi, PM_WC)][2]
-  int32_t* t_start = reinterpret_cast<int32_t*>(wbase + (size_t)pm_staged_words(a.wi) * 32 * 2 * sizeof(float4));
-  int32_t* t_b1 = t_start + 9;
-  int32_t* t_b2 = t_b1 + 9;
-  int32_t* t_pre = t_b2 + 9;  // [10]
-  float4* t_rc = reinterpret_cast<float4*>(t_start + 40);  // [27], index run * 3 + column
+  int4* t_run = reinterpret_cast<int4*>(wbase + (size_t)pm_staged_words(a.wi) * 32 * 2 * sizeof(float4));  // [9]
+  float4* t_rc = reinterpret_cast<float4*>(t_run + 9);  // [27], index run * 3 + column
 
   const GridParams<T>& gp = a.gp;
   const int32_t mx = gp.mesh[0], my = gp.mesh[1], mz = gp.mesh[2];
@@ -718,6 +716,7 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
       axis_range(cz, mz, zlo, zhi);
       const int32_t ny = yhi - ylo + 1, nruns = ny * (zhi - zlo + 1);
       __syncwarp();  // the previous cell's readers are done
+      int32_t nj;  // candidates of this cell = particles of its stencil
       // the first two words of the cell's own particles are requested now, next to the run table's cell starts: one
       // round trip instead of two before the first candidate can be set up
       float4 pre_i[2];
@@ -746,12 +745,8 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
           const int32_t v = __shfl_up_sync(0xffffffffu, incl, d);
           if (lane >= d) incl += v;
         }
-        if (lane < 9) {
-          t_start[lane] = s0;
-          t_b1[lane] = b1;
-          t_b2[lane] = b2;
-        }
-        if (lane < 10) t_pre[lane] = incl - len;  // lane 9: len = 0 -> the total
+        if (lane < 9) t_run[lane] = make_int4(incl, s0 - (incl - len), b1, b2);  // absent runs: len 0, end = total
+        nj = __shfl_sync(0xffffffffu, incl, 8);
         // lane e = run * 3 + column writes that stencil cell's entry: everything a candidate's set-up needs from its
         // cell comes from ONE 16-byte shared-memory load instead of six look-ups and the selects between them
         const int er = lane / 3, ecol = lane - er * 3;
@@ -764,7 +759,6 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
         }
       }
       __syncwarp();
-      const int32_t nj = t_pre[9];
       if (lane == 0 && part == 0) cand_local += (unsigned long long)ni * (unsigned long long)nj;
 
       for (int32_t iw0 = 0; iw0 * 32 < ni; iw0 += PM_WC) {  // one round for cells of up to 256 particles
@@ -778,28 +772,29 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
         si[2 * (k - iw0 * 32) + 1] = make_float4(z, z, nai, nai);
       }
       __syncwarp();
+      // cursor into the run table: a lane's candidates ascend over the chunks, so the run only moves forward and the
+      // table is read again (one 16-byte load) only when a candidate crosses into the next run
+      int32_t run = 0;
+      int4 cur = t_run[0];
       for (int32_t c0 = part * (32 * PM_RJ); c0 < nj; c0 += a.parts * (32 * PM_RJ)) {
         float xj[PM_RJ], yj[PM_RJ], zj[PM_RJ], wj[PM_RJ];
         int32_t sj[PM_RJ];  // candidate's slot
         int32_t oj[PM_RJ];  // its mask plane for this cell (o * wi); -1: tail lane or ghost row, nothing to store
         int32_t pj[PM_RJ];  // HALFIDS: particles of this cell with an id <= the candidate's (they are not kept)
-        // three passes so that the PM_RJ record loads are in flight together: slots first (shared-memory look-ups
-        // only), then every load, then the translation — the run look-up loop between two loads used to serialise
-        // them into PM_RJ round trips per chunk
+        // three passes so that the PM_RJ record loads are in flight together: slots first (run table only), then
+        // every load, then the translation — the run look-up between two loads used to serialise them into PM_RJ
+        // round trips per chunk
         int32_t rcol[PM_RJ];  // run * 3 + column; -1: tail lane
-        {
-          int r = 0;
 #pragma unroll
-          for (int k = 0; k < PM_RJ; k++) {
-            const int32_t c = c0 + k * 32 + lane;
-            sj[k] = 0;
-            rcol[k] = -1;
-            if (c < nj) {
-              while (c >= t_pre[r + 1]) r++;
-              const int32_t s = t_start[r] + (c - t_pre[r]);
-              sj[k] = s;
-              rcol[k] = r * 3 + ((s >= t_b1[r]) ? 1 : 0) + ((s >= t_b2[r]) ? 1 : 0);
-            }
+        for (int k = 0; k < PM_RJ; k++) {
+          const int32_t c = c0 + k * 32 + lane;
+          sj[k] = 0;
+          rcol[k] = -1;
+          if (c < nj) {
+            while (c >= cur.x) cur = t_run[++run];  // c < nj = end of run 8: stops at run <= 8
+            const int32_t s = cur.y + c;
+            sj[k] = s;
+            rcol[k] = run * 3 + ((s >= cur.z) ? 1 : 0) + ((s >= cur.w) ? 1 : 0);
           }
         }
         float4 rjv[PM_RJ];
