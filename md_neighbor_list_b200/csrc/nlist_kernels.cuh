@@ -660,7 +660,8 @@ constexpr int PM_TAB = 9 * 4 + 27 * 4;
 constexpr int PM_WC = 8;
 __host__ __device__ inline int pm_staged_words(int wi) { return wi < PM_WC ? wi : PM_WC; }
 __host__ __device__ inline size_t pm_warp_bytes(int wi) {
-  return (size_t)pm_staged_words(wi) * 32 * 2 * sizeof(float4) + PM_TAB * 4;
+  // staged particles {xi,xi,yi,yi},{zi,zi,-ai,-ai} + the tables + the staged particles' ids (HALF lists)
+  return (size_t)pm_staged_words(wi) * 32 * (2 * sizeof(float4) + sizeof(int32_t)) + PM_TAB * 4;
 }
 
 #ifndef NLB_PM_MINB
@@ -679,6 +680,7 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
   float4* si = reinterpret_cast<float4*>(wbase);  // [32 * min(wi, PM_WC)][2]
   int4* t_run = reinterpret_cast<int4*>(wbase + (size_t)pm_staged_words(a.wi) * 32 * 2 * sizeof(float4));  // [9]
   float4* t_rc = reinterpret_cast<float4*>(t_run + 9);  // [27], index run * 3 + column
+  int32_t* sid = reinterpret_cast<int32_t*>(t_rc + 27);  // [32 * staged words]: ids of the staged particles, ascending
 
   const GridParams<T>& gp = a.gp;
   const int32_t mx = gp.mesh[0], my = gp.mesh[1], mz = gp.mesh[2];
@@ -770,6 +772,7 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
         const float nai = -0.5f * (fmaf(x, x, fmaf(y, y, z * z)) - gp.sl2f);
         si[2 * (k - iw0 * 32)] = make_float4(x, x, y, y);
         si[2 * (k - iw0 * 32) + 1] = make_float4(z, z, nai, nai);
+        if (HALFIDS) sid[k - iw0 * 32] = __float_as_int(r.w);
       }
       __syncwarp();
       // cursor into the run table: a lane's candidates ascend over the chunks, so the run only moves forward and the
@@ -816,19 +819,25 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
             // rec.w carries the particle's local id (cellsort_kernel): rows of ghosts (id >= n_owned) are not stored
             const int32_t idj = __float_as_int(rj.w);
             if (idj < a.n_owned) oj[k] = __float_as_int(tr.w);
-            if (HALFIDS) {
-              // upper bound of idj in the cell's ascending ids
-              int32_t lo = 0, hi = ni;
-              while (lo < hi) {
-                const int32_t mid = (lo + hi) >> 1;
-                if (__ldg(a.sorted_ids + ibeg + mid) <= idj)
-                  lo = mid + 1;
-                else
-                  hi = mid;
-              }
-              pj[k] = lo;
+          }
+        }
+        if (HALFIDS) {
+          // pj = number of this cell's particles with an id <= the candidate's: upper bound in the ascending ids of the
+          // staged particles (shared memory), branch-free and with the PM_RJ searches of a lane interleaved step by
+          // step — a binary search per candidate in global memory cost a third of the kernel
+          const int32_t nwin = min(ni, iw1 * 32) - iw0 * 32;
+          int32_t pos[PM_RJ];
+#pragma unroll
+          for (int k = 0; k < PM_RJ; k++) pos[k] = 0;
+          for (int32_t step = 1 << (31 - __clz(nwin)); step > 0; step >>= 1) {
+#pragma unroll
+            for (int k = 0; k < PM_RJ; k++) {
+              const int32_t t = pos[k] + step;
+              if (t <= nwin && sid[min(t, nwin) - 1] <= __float_as_int(rjv[k].w)) pos[k] = t;
             }
           }
+#pragma unroll
+          for (int k = 0; k < PM_RJ; k++) pj[k] = iw0 * 32 + pos[k];
         }
         f32x2 X[PM_RJ / 2], Y[PM_RJ / 2], Z[PM_RJ / 2], W[PM_RJ / 2];
 #pragma unroll
