@@ -1036,23 +1036,24 @@ __global__ void __launch_bounds__(128) rowcount_kernel(EmitArgs a) {
   axis_range(bz, mz, zlo, zhi);
   const int32_t nx = xhi - xlo + 1, ny = yhi - ylo + 1, nz = zhi - zlo + 1;
   const uint32_t* mrow = a.mask + slot;
-  const bool two = a.wi >= 2;
+  const long long cell_stride = (long long)a.wi * a.n_cap;  // words between the planes of two stencil cells
+  const long long word1 = a.wi >= 2 ? a.n_cap : 0;           // second word of a cell (wi = 1: the first one again)
+  const uint32_t* mcell = mrow;  // walks the stencil cells' planes in order
   int32_t cnt = 0;
   for (int oz = 0; oz < nz; oz++) {
+    // unconditional loads at clamped addresses (as in emit_kernel): cells the row does not have are dropped by nw = 0
     int32_t cbp[3][4];
     uint32_t mp[3][3][2];
 #pragma unroll
     for (int oy = 0; oy < 3; oy++) {
-      const bool rv = oy < ny;
-      const int32_t* cs = a.cell_start + ((ylo + oy) + (zlo + oz) * my) * mx + xlo;
+      const int32_t* cs = a.cell_start + (min(ylo + oy, my - 1) + (zlo + oz) * my) * mx + xlo;
 #pragma unroll
-      for (int k = 0; k < 4; k++) cbp[oy][k] = (rv && k <= nx) ? __ldg(cs + k) : 0;
-      const int32_t o0 = (oz * 3 + oy) * 3 * a.wi;
+      for (int k = 0; k < 4; k++) cbp[oy][k] = __ldg(cs + min(k, nx));
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        const bool cv = rv && k < nx;
-        mp[oy][k][0] = cv ? __ldg(mrow + (long long)(o0 + k * a.wi) * a.n_cap) : 0u;
-        mp[oy][k][1] = (cv && two) ? __ldg(mrow + (long long)(o0 + k * a.wi + 1) * a.n_cap) : 0u;
+        mp[oy][k][0] = __ldg(mcell);
+        mp[oy][k][1] = __ldg(mcell + word1);
+        mcell += cell_stride;
       }
     }
 #pragma unroll
@@ -1210,27 +1211,31 @@ __global__ void __launch_bounds__(EM_WARPS * 32, NLB_EM_MINB) emit_kernel(EmitAr
   axis_range(bz, mz, zlo, zhi);
   const int32_t nx = owned ? xhi - xlo + 1 : 0, ny = yhi - ylo + 1, nz = zhi - zlo + 1;
   const int32_t own = owned ? slot - __ldg(a.cell_start + cell) : 0;
-  const uint32_t* mrow = a.mask + slot;
-  const bool two = a.wi >= 2;
+  const uint32_t* mrow = a.mask + min((long long)slot, a.n_cap - 1);  // lanes past the last slot load in range
+  const long long cell_stride = (long long)a.wi * a.n_cap;  // words between the planes of two stencil cells
+  const long long word1 = a.wi >= 2 ? a.n_cap : 0;           // second word of a cell (wi = 1: the first one again)
 
   // the plane / run loops are warp-uniform (3 x 3 stencil ordinals); lanes without that run see empty words
+  const uint32_t* mcell = mrow;  // walks the 27 stencil cells' planes in order
   for (int oz = 0; oz < 3; oz++) {
     // all loads of the plane (3 runs x (4 cell starts + 6 words)) are issued before any is used; the word loads do
-    // not wait for the cell starts (words beyond a cell's population are discarded afterwards)
+    // not wait for the cell starts (words beyond a cell's population are discarded afterwards).  Every load is
+    // unconditional with an address clamped into the arrays — stencil cells a boundary row does not have read
+    // planes nobody wrote, and their words are dropped by nw = 0 below — and the mask pointer advances by one
+    // 64-bit add per cell: the predicated loads with a 64-bit multiply each were a tenth of the kernel's instructions
     int32_t cbp[3][4];
     uint32_t mp[3][3][2];
+    const int32_t zz = min(zlo + oz, mz - 1);
 #pragma unroll
     for (int oy = 0; oy < 3; oy++) {
-      const bool rv = (nx > 0) && (oz < nz) && (oy < ny);
-      const int32_t* cs = a.cell_start + ((ylo + oy) + (zlo + oz) * my) * mx + xlo;
+      const int32_t* cs = a.cell_start + (min(ylo + oy, my - 1) + zz * my) * mx + xlo;
 #pragma unroll
-      for (int k = 0; k < 4; k++) cbp[oy][k] = (rv && k <= nx) ? __ldg(cs + k) : 0;
-      const int32_t o0 = (oz * 3 + oy) * 3 * a.wi;
+      for (int k = 0; k < 4; k++) cbp[oy][k] = __ldg(cs + min(k, nx));
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        const bool cv = rv && k < nx;
-        mp[oy][k][0] = cv ? __ldg(mrow + (long long)(o0 + k * a.wi) * a.n_cap) : 0u;
-        mp[oy][k][1] = (cv && two) ? __ldg(mrow + (long long)(o0 + k * a.wi + 1) * a.n_cap) : 0u;
+        mp[oy][k][0] = __ldg(mcell);
+        mp[oy][k][1] = __ldg(mcell + word1);
+        mcell += cell_stride;
       }
     }
 #pragma unroll
