@@ -432,6 +432,8 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     em.global_ids = gids;
     em.slot_pid = gids != nullptr ? h->slot_gid : h->sorted_ids;
     for (int d = 0; d < 3; d++) em.mesh[d] = gp.mesh[d];
+    em.d_mx = make_fastdiv((uint32_t)gp.mesh[0]);
+    em.d_my = make_fastdiv((uint32_t)gp.mesh[1]);
     em.n_total = n;
     em.n_owned = (int32_t)n_owned;
     em.n_cells = M;

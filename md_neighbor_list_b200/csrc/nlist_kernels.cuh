@@ -954,6 +954,7 @@ struct EmitArgs {
   const int32_t* global_ids;  // optional local -> global id map (HALF rule of the row's own particle)
   const int32_t* slot_pid;    // partner id reported for a slot: sorted_ids, or the global ids in slot order
   int32_t mesh[3];
+  FastDiv d_mx, d_my;  // cell -> (bx, by, bz) without hardware divisions
   int32_t n_total, n_owned;
   int32_t n_cells;  // cell_start[n_cells] = particles present (n_total minus absent ghosts) = slots in use
   int32_t clear_self;  // 1: a row's own bit is set in the masks and has to be dropped (FULL lists)
@@ -1019,8 +1020,8 @@ __device__ __forceinline__ void walk_words(const EmitArgs& a, int32_t slot, int3
 
 // FULL lists: the row length is a popcount of the row's mask words (without its own bit).  Thread = row.  All loads
 // of a stencil plane (12 cell starts + 18 words) are issued before any is used and the word loads do not wait for the
-// cell starts — the kernel is bound by load latency, not by the 26 MB it reads from L2 (walk_words, one x-run at a
-// time with the words behind the cell starts, took 9 x 2 dependent round trips per row: 14 us vs this form's 3).
+// cell starts.  The kernel is bound by its own index arithmetic (it issues on half of the cycles for 26 MB of L2
+// reads), which is why the loads are unconditional and the plane pointer is a running 64-bit add.
 __global__ void __launch_bounds__(128) rowcount_kernel(EmitArgs a) {
   pdl_enter();
   const int32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1029,7 +1030,8 @@ __global__ void __launch_bounds__(128) rowcount_kernel(EmitArgs a) {
   if (id >= a.n_owned) return;
   const int32_t cell = __ldg(a.slot_cell + slot);
   const int32_t mx = a.mesh[0], my = a.mesh[1], mz = a.mesh[2];
-  const int32_t bx = cell % mx, by = (cell / mx) % my, bz = cell / (mx * my);
+  const int32_t byz = (int32_t)fdiv((uint32_t)cell, a.d_mx), bx = cell - byz * mx;
+  const int32_t bz = (int32_t)fdiv((uint32_t)byz, a.d_my), by = byz - bz * my;
   int xlo, xhi, ylo, yhi, zlo, zhi;
   axis_range(bx, mx, xlo, xhi);
   axis_range(by, my, ylo, yhi);
@@ -1204,7 +1206,8 @@ __global__ void __launch_bounds__(EM_WARPS * 32, NLB_EM_MINB) emit_kernel(EmitAr
   };
 
   const int32_t mx = a.mesh[0], my = a.mesh[1], mz = a.mesh[2];
-  const int32_t bx = cell % mx, by = (cell / mx) % my, bz = cell / (mx * my);
+  const int32_t byz = (int32_t)fdiv((uint32_t)cell, a.d_mx), bx = cell - byz * mx;
+  const int32_t bz = (int32_t)fdiv((uint32_t)byz, a.d_my), by = byz - bz * my;
   int xlo, xhi, ylo, yhi, zlo, zhi;
   axis_range(bx, mx, xlo, xhi);
   axis_range(by, my, ylo, yhi);
