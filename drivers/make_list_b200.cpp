@@ -1,10 +1,15 @@
 // make_list_b200.cpp — a driver of the reference's shape (make_list.cu:102-201 for the GPU class, make_list.cpp:132-226
 // for the CPU classes) built on include/nlist_b200_shim.hpp: generate the jittered-FCC default system, build the list
 // LOOP times, print "# of particles N T[ms]", then verify against an O(N^2) brute force and print "TEST is passed."
-// usage: make_list_b200.out [gpu|cpu] [density] [loop] [check]
+// usage: make_list_b200.out [gpu|cpu|md] [density] [loop] [check]
 //   gpu : NeighListGPU interface (full list, list[k*N + i] layout)     cpu : NeighList interface (half list, CSR)
+//   md  : what the drivers' unused momenta `p` are for (make_list.cpp:135-140): LOOP velocity-Verlet steps of a
+//         Lennard-Jones system in a 20^3 box on the NeighListGPU interface — forces from the list on the device, the
+//         list rebuilt only when a particle has moved more than margin / 2 since the last build
+//         — then the forces of the (possibly several steps old) list are checked against an O(N^2) evaluation
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -53,9 +58,97 @@ void bruteforce(const std::vector<double4v>& q, bool full, std::vector<int32_t>&
   for (int i = 0; i < n; i++) std::copy(rows[i].begin(), rows[i].end(), list.begin() + kp[i]);
 }
 
+// Lennard-Jones forces by brute force: every pair inside rc, plain Euclidean distance (no minimum image, like the list)
+void lj_bruteforce(const std::vector<double4v>& q, double rc, double eps, double sigma, std::vector<double>& f) {
+  const int n = (int)q.size();
+  f.assign((std::size_t)3 * n, 0.0);
+  const double rc2 = rc * rc, s2 = sigma * sigma;
+  for (int i = 0; i < n; i++)
+    for (int j = i + 1; j < n; j++) {
+      const double dx = q[i].x - q[j].x, dy = q[i].y - q[j].y, dz = q[i].z - q[j].z;
+      const double r2 = dx * dx + dy * dy + dz * dz;
+      if (!(r2 < rc2) || r2 == 0.0) continue;
+      const double sr2 = s2 / r2, sr6 = sr2 * sr2 * sr2;
+      const double fr = 24.0 * eps * sr6 * (2.0 * sr6 - 1.0) / r2;
+      f[3 * i] += fr * dx; f[3 * i + 1] += fr * dy; f[3 * i + 2] += fr * dz;
+      f[3 * j] -= fr * dx; f[3 * j + 1] -= fr * dy; f[3 * j + 2] -= fr * dz;
+    }
+}
+
+int run_md(double density, int steps) {
+  const double Lmd = 20.0, RC = 3.0, MARGIN = SEARCH_LENGTH - RC, DT = 0.002;
+  const int64_t n64 = nlb200_workload_fcc(density, Lmd, 0, 0, 0, 2, nullptr, 4, 0);
+  const int32_t N = (int32_t)n64;
+  nlb200::cuda_ptr<double4v> q;
+  q.allocate(N);
+  nlb200_workload_fcc(density, Lmd, 0, 0, 0, 2, &q[0].x, 4, N);
+  std::vector<double> p((std::size_t)3 * N);  // the momenta of make_list.cpp:135-140, finally used
+  unsigned long long rng = 2;
+  for (auto& v : p) {
+    rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+    v = ((double)(rng >> 11) / 9007199254740992.0 - 0.5) * 2.0;
+  }
+  q.host2dev();
+  nlb200::cuda_ptr<double> f;
+  f.allocate((std::size_t)3 * N);
+  nlb200::NeighListGPU<double4v, double> nl(SEARCH_LENGTH, Lmd, Lmd, Lmd);
+  nl.Initialize(N);
+  nl.MakeNeighList(q, N, true);
+  nl.TrackReference(q);
+  int builds = 1;
+  double max_seen = 0.0;
+  nl.LJForces(q, RC, 1.0, 1.0, f);
+  f.dev2host();
+  for (int s = 0; s < steps; s++) {
+    // velocity Verlet, half kick + drift on the host (the demo's point is the list, not the integrator); particles are
+    // kept inside the open box by reflection
+    for (int i = 0; i < N; i++) {
+      double* x = &q[i].x;
+      for (int d = 0; d < 3; d++) {
+        p[3 * i + d] += 0.5 * DT * f[3 * i + d];
+        x[d] += DT * p[3 * i + d];
+        if (x[d] < 0.0) { x[d] = -x[d]; p[3 * i + d] = -p[3 * i + d]; }
+        if (x[d] > Lmd) { x[d] = 2.0 * Lmd - x[d]; p[3 * i + d] = -p[3 * i + d]; }
+      }
+    }
+    q.host2dev();
+    const double disp = nl.MaxDisplacement(q);
+    max_seen = std::max(max_seen, disp);
+    if (disp > 0.5 * MARGIN) {  // some particle left the safety shell: the list may miss a pair inside rc
+      nl.MakeNeighList(q, N, true);
+      nl.TrackReference(q);
+      builds++;
+    }
+    nl.LJForces(q, RC, 1.0, 1.0, f);
+    f.dev2host();
+    for (int i = 0; i < 3 * N; i++) p[i] += 0.5 * DT * f[i];
+  }
+  std::printf("# of particles %d, %d steps, %d list builds, largest displacement seen %.4f (margin/2 = %.3f)\n", N, steps,
+              builds, max_seen, 0.5 * MARGIN);
+  // forces from the list in use (built up to steps/builds steps ago) against every pair inside rc
+  std::vector<double4v> qh(N);
+  for (int i = 0; i < N; i++) qh[i] = q[i];
+  std::vector<double> fref;
+  lj_bruteforce(qh, RC, 1.0, 1.0, fref);
+  double worst = 0.0, scale = 1e-300;
+  for (int i = 0; i < 3 * N; i++) {
+    worst = std::max(worst, std::fabs(f[i] - fref[i]));
+    scale = std::max(scale, std::fabs(fref[i]));
+  }
+  if (!(worst <= 1e-9 * scale)) {
+    std::fprintf(stderr, "TEST fail lj_forces %.3e (scale %.3e)\n", worst, scale);
+    return 1;
+  }
+  if (builds < 2 || builds > steps / 2) return fail("list_builds", builds, steps);
+  std::fprintf(stderr, "TEST is passed.\n");
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
+  if (argc > 1 && std::strcmp(argv[1], "md") == 0)
+    return run_md(argc > 2 ? std::atof(argv[2]) : 1.0, argc > 3 ? std::atoi(argv[3]) : 200);
   const bool gpu = argc < 2 || std::strcmp(argv[1], "cpu") != 0;
   const double density = argc > 2 ? std::atof(argv[2]) : 1.0;
   const int LOOP = argc > 3 ? std::atoi(argv[3]) : 100;  // make_list.cpp:21

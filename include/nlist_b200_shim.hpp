@@ -175,6 +175,35 @@ class NeighListGPU {
   }
   nlb200_handle handle() { return h_; }
 
+  // ---- the callers either side of the build: what a driver does with the list -------------------
+  // f2, Verlet-list lifetime: SEARCH_LENGTH includes a margin (make_list.cpp:23) so that a list survives until some
+  // particle has moved margin / 2; the reference's drivers rebuild 100 times instead (make_list.cpp:153-155).
+  void TrackReference(cuda_ptr<Vec>& q) { check(nlb200_track_reference(h_, q.dev(), n_, stream_), "TrackReference"); }
+  double MaxDisplacement(cuda_ptr<Vec>& q) {
+    double d = 0.0;
+    check(nlb200_max_displacement(h_, q.dev(), n_, stream_, &d), "MaxDisplacement");
+    return d;
+  }
+  bool NeedsRebuild(cuda_ptr<Vec>& q, const Dtype margin) { return MaxDisplacement(q) > 0.5 * (double)margin; }
+  // f4, a consumer of the FULL rows: Lennard-Jones forces f[3N] (and per-particle energies) with cutoff rc <= search
+  // length — the momenta `p` the reference allocates and never uses (make_list.cpp:135-140) get their forces here.
+  void LJForces(cuda_ptr<Vec>& q, const double rc, const double epsilon, const double sigma, cuda_ptr<double>& forces,
+                cuda_ptr<double>* energy = nullptr) {
+    synchronize();
+    check(nlb200_lj_forces(h_, q.dev(), rc, epsilon, sigma, forces.dev(), energy ? energy->dev() : nullptr, stream_),
+          "LJForces");
+    cuda_or_die(cudaStreamSynchronize(stream_), "LJForces");
+  }
+  // f1, the physical reorder the reference stubbed out (SortPtclData, neighlist_cpu.hpp:176-180; CopyGather,
+  // neighlist_gpu.hpp:144-151): dst[slot] = src[cell order of the last build], `width` elements of T per particle.
+  template <typename T>
+  void GatherSorted(cuda_ptr<T>& src, cuda_ptr<T>& dst, const int width) {
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "4- or 8-byte elements");
+    synchronize();
+    check(nlb200_gather_sorted(h_, src.dev(), (int)sizeof(T), width, dst.dev(), stream_), "GatherSorted");
+    cuda_or_die(cudaStreamSynchronize(stream_), "GatherSorted");
+  }
+
  private:
   void check(int st, const char* what) {
     if (st) die(h_, st, what);

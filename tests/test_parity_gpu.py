@@ -552,6 +552,20 @@ def test_cpp_driver_self_test(cuda, iface, dens):
     assert "# of particles 62500" in r.stdout
 
 
+def test_cpp_driver_md_loop(cuda):
+    """drivers/make_list_b200.cpp md: velocity-Verlet steps on the C++ shim (NeighListGPU::LJForces, TrackReference,
+    MaxDisplacement): the list is rebuilt only when a particle moved more than margin/2, and the forces of the list in
+    use equal an O(N^2) evaluation over every pair inside the cutoff."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "drivers", "make_list_b200.out")
+    if not os.path.exists(exe):
+        pytest.fail("drivers/make_list_b200.out is missing: run __graft_entry__.build()")
+    r = subprocess.run([exe, "md", "1.0", "200"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "TEST is passed." in r.stderr
+    assert "list builds" in r.stdout
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # callers either side of the build (SURVEY.md §8f f1, f2)
 # ---------------------------------------------------------------------------------------------------------------
