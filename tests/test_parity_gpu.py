@@ -538,6 +538,20 @@ def test_kernel_variants_emit_identical_lists(cuda, oracle, mode):
     assert_matches(oracle, outs[2], ref)
 
 
+def test_programmatic_dependent_launch_gives_the_same_list(cuda, oracle, monkeypatch):
+    """NLB200_OPT_PDL (environment override NLB200_PDL=1): the kernels of a build chained by programmatic dependent
+    launch instead of plain stream order — graph replay and plain launches — must not change a bit of the result."""
+    from md_neighbor_list_b200 import workloads
+    L = 20.0
+    q = workloads.fcc(1.0, L)
+    ref = oracle.build_full(q, 3.3, (L, L, L))
+    monkeypatch.setenv("NLB200_PDL", "1")
+    for use_graph in (True, False):
+        got = gpu_build(cuda, q, 3.3, (L, L, L), "full_csr", builds=3, use_graph=use_graph)
+        assert_matches(oracle, got, ref)
+        got["handle"].close()
+
+
 @pytest.mark.parametrize("iface, dens", [("gpu", 0.5), ("cpu", 0.5)])
 def test_cpp_driver_self_test(cuda, iface, dens):
     """drivers/make_list_b200.cpp: the reference drivers' own protocol (build LOOP times, O(N^2) brute force, compare
