@@ -579,7 +579,12 @@ __global__ void __launch_bounds__(128) search_kernel(SearchArgs<T> a) {
 //                     SL of j" — by symmetry a piece of ROW j.  Only a word whose min|d| fell inside the uncertainty
 //                     band E is revisited (by the whole warp, lane = particle) with the exact input-precision test.
 //                     mask[o][w][slot_j]: o = ordinal of A inside the stencil of j's cell, w = word (32 i's each).
-//                     HALFIDS: the id filter of HALF lists is a suffix cut per (candidate, cell), see the kernel.
+//                     Candidate set-up is table-driven: per item the warp builds 9 int4 run entries and 27 float4
+//                     (run, column) entries in shared memory; a lane keeps a cursor into the run table in registers,
+//                     issues its PM_RJ record loads together and takes translation + mask plane from one 16-byte
+//                     entry.  Integer divisions by mesh extents / parts are multiply-high (FastDiv).
+//                     HALFIDS: the id filter of HALF lists is a suffix cut per (candidate, cell), found by a
+//                     branch-free upper-bound search over the staged ids in shared memory, see the kernel.
 //   rowcount_kernel   thread = row: popcount of the row's <= 27*WI words.
 //   scan_kernel       counts -> offsets (as before).
 //   emit_kernel       thread = row: expands set bits MSB-first (FLO) into its line of a per-warp shared-memory tile;
@@ -1114,17 +1119,18 @@ __global__ void __launch_bounds__(128) emit_direct_kernel(EmitArgs a) {
 }
 
 // emit_kernel: thread = row, warp = 32 consecutive cell-sorted slots; warps are independent (no CTA barrier).
-//   Each lane expands the set bits of its row's words, MSB first (FLO), into its line of a [32][EM_TILE] shared-memory
-//   tile; the three cells of an x-run are expanded as three interleaved dependency chains whose write positions
-//   follow from popcounts.  When a line could overflow, the warp flushes the tile: row by row, the staged cell-sorted
-//   slots are turned into partner ids (gather from sorted_ids / global_ids) and stored with coalesced 128-byte
-//   stores at partners[offsets[id] + done ...].  4 KB of tile per warp instead of whole rows keeps ~24 warps per SM
-//   resident; the expansion is a chain of dependent ALU/XU ops and needs that many to hide its latency.
+//   Each lane expands the set bits of its row's words, MSB first (one FLO per bit), into its line of a
+//   [32][EM_TILE] shared-memory tile: the cell-sorted SLOTS of its partners, cell by cell in stencil order.  When a
+//   line could overflow (checked per cell), every lane flushes ITS OWN line to its row: slots -> partner ids (gather
+//   from sorted_ids / the per-slot global ids), scalar stores until the row position is 16-byte aligned, then 16-byte
+//   vector stores at partners[offsets[id] + done ...]; the <= 3 entries that do not fill a vector stay in the line.
+//   7 KB of tile per warp instead of whole rows keeps 28 warps per SM resident (72 registers), which is all the
+//   25 warps of rows an SM gets on the default system.
 // Rejected (measured): one warp per (32 rows, stencil plane) — three times the warps, a third of the serial chain per
 // lane — emits the default system in 77.7 us vs 75.9 us: the kernel is not short of parallelism, its issue slots, XU
 // (FLO) and LSU wavefronts are each ~40-50 % busy.
 // HALF:  rows keep the partners with a larger (global) id (neighlist_cpu.hpp:225-236); the filter runs in the flush
-//        (ballot compaction).  COUNT: write counts[id] instead of partners (HALF lists need the ids to count).
+//        (scalar stores of the kept ids).  COUNT: write counts[id] instead of partners (HALF lists need the ids to count).
 #ifndef NLB_EM_WARPS
 #define NLB_EM_WARPS 2
 #endif
