@@ -1,5 +1,6 @@
 """Times one workload (not the headline bench): python tools/bench_workload.py KIND N [mode] [reps]
-KIND: uniform | fcc | clustered.  Prints ms/build (graph replay, L2-cold), stage times and throughput."""
+KIND: uniform | fcc | clustered (fcc: N is the box edge; density from the environment variable DENSITY, default 1.0).
+Prints ms/build (graph replay, L2-cold), stage times and throughput."""
 import json
 import os
 import sys
@@ -20,7 +21,7 @@ if kind == "uniform":
     q = workloads.uniform(n, L)
 elif kind == "fcc":
     L = float(n)  # here N is the box edge
-    q = workloads.fcc(1.0, L)
+    q = workloads.fcc(float(os.environ.get("DENSITY", "1.0")), L)
 else:
     L = float(round(n ** (1.0 / 3.0)))
     q = workloads.clustered(n, L)
