@@ -422,7 +422,8 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     pm.mask = h->mask;
     pm.n_cap = h->mask_ncap;
     pm.wi = h->mask_wi;
-    pm.fits32 = (27ll * h->mask_wi * h->mask_ncap) < (1ll << 32) ? 1 : 0;
+    // variant 7 (test hook): the 64-bit index path that masks of >= 2^32 words (> 53 M particles at 3 words) take
+    pm.fits32 = ((27ll * h->mask_wi * h->mask_ncap) < (1ll << 32) && h->variant != 7) ? 1 : 0;
     pm.band = gp.band;
     pm.st = h->status_dev;
     EmitArgs em;

@@ -244,6 +244,15 @@ def test_clustered_heavy_cells(cuda, oracle):
     assert_matches(oracle, got, oracle.build_full(q, 2.3, box))
     got = gpu_build(cuda, q, 2.3, box, "half_csr")
     assert_matches(oracle, got, oracle.build_half(q, 2.3, box))
+    # cells of more than 256 particles: the pair-mask kernel stages a cell in several rounds (run cursor and the
+    # HALF id cut restart per round)
+    q = workloads.clustered(3000, 18.0, blobs=2)
+    box = (18.0, 18.0, 18.0)
+    got = gpu_build(cuda, q, 2.3, box, "full_csr")
+    assert got["max_in_cell"] > 256
+    assert_matches(oracle, got, oracle.build_full(q, 2.3, box))
+    got = gpu_build(cuda, q, 2.3, box, "half_csr")
+    assert_matches(oracle, got, oracle.build_half(q, 2.3, box))
 
 
 def test_out_of_box_and_nan_are_reported(cuda):
@@ -525,13 +534,15 @@ def test_kernel_variants_emit_identical_lists(cuda, oracle, mode):
     q = workloads.fcc(1.0, 23.0)
     box = (23.0, 23.0, 23.0)
     # 4 = HALF rows filtered by id during the emission (the multi-GPU path) instead of inside the masks
-    outs = [gpu_build(cuda, q, 3.3, box, mode, kernel_variant=v) for v in (1, 2, 3, 4)]
+    # 7 = mask indices in 64-bit arithmetic (the path of systems whose masks exceed 2^32 words)
+    outs = [gpu_build(cuda, q, 3.3, box, mode, kernel_variant=v) for v in (1, 2, 3, 4, 7)]
     for o in outs[1:]:
         assert o["pairs"] == outs[0]["pairs"]
         assert np.array_equal(o["np"], outs[0]["np"])
         assert np.array_equal(o["off"], outs[0]["off"])
     assert np.array_equal(outs[1]["list"], outs[2]["list"])
     assert np.array_equal(outs[1]["list"], outs[3]["list"])
+    assert np.array_equal(outs[1]["list"], outs[4]["list"])
     if mode == "full_csr":
         assert np.array_equal(outs[0]["list"], outs[1]["list"])
     ref = oracle.build_full(q, 3.3, box) if mode == "full_csr" else oracle.build_half(q, 3.3, box)
