@@ -1,7 +1,6 @@
 # round-end validation on the GPU box: full GPU test suite, C++ driver self-tests, both bench arms, the ncu launch list
 # of the bench command and one full ncu capture of the build's kernels (each only after its command exited 0 plainly)
 set -u
-R=${ROUND_TAG:-r01}
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print(\"smoke ok\")" 2>&1 | tail -2
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_final.txt 2>&1; tail -3 gpurun_out/pytest_final.txt
 ./drivers/make_list_b200.out gpu 1.0 100 1 > gpurun_out/driver_gpu.txt 2>&1; tail -2 gpurun_out/driver_gpu.txt
