@@ -139,3 +139,90 @@ def test_single_rank_is_a_no_op():
     g = torch.arange(100, dtype=torch.int32)
     qa, ga, n = dec.exchange(q, g)
     assert n == 100 and qa is q and ga is g and dec.max_ghosts(100) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# periodic ring: minimum-image rows over world slabs
+# ---------------------------------------------------------------------------------------------------------------
+def _periodic_system(world: int):
+    rng = np.random.default_rng(7)
+    box = (11.0, 12.5, 7.5 * world)
+    n = 700 * world
+    q = np.zeros((n, 4))
+    q[:, :3] = rng.random((n, 3)) * np.array(box)
+    # particles on the faces and just inside them, on every axis
+    q[0, :3] = (0.0, 0.0, 0.0)
+    q[1, :3] = (box[0] - 1e-9, box[1] - 1e-9, box[2] - 1e-9)
+    q[2, :3] = (5.0, 6.0, 7.5)  # exactly on the seam between slab 0 and slab 1
+    return q, box
+
+
+def _minimum_image_rows(q, box, rows_of):
+    L = np.array(box)
+    out = []
+    for i in rows_of:
+        d = q[:, :3] - q[i, :3]
+        d -= L * np.round(d / L)
+        r2 = (d * d).sum(axis=1)
+        m = r2 <= SL * SL
+        m[i] = False
+        out.append(np.nonzero(m)[0])
+    return out
+
+
+def _periodic_worker(rank: int, world: int, port: int):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from md_neighbor_list_b200.periodic import PeriodicSlabDecomposition
+        from oracle import oracle as O
+        q, box = _periodic_system(world)
+        dec = PeriodicSlabDecomposition(world, rank, box, SL, axis=2)
+        q_own, gid_own = dec.partition(q)
+        assert q_own.shape[0] > 0
+        ext = dec.extended_box()
+
+        def build_fn(q_all, n_owned, gid_all):
+            qa, ga = q_all.numpy(), gid_all.numpy()
+            assert qa.shape[0] == dec.n_total(n_owned)
+            present = ~np.isnan(qa[:, 0])
+            assert present[:n_owned].all()
+            qa, ga = qa[present], ga[present]
+            # every record lies inside the extended box and is a periodic copy of the particle whose id it carries
+            assert (qa[:, :3] >= 0).all() and (qa[:, :3] < np.array(ext)).all()
+            d = qa[:, :3] - SL - q[ga, :3]
+            assert np.abs(d - np.array(box) * np.round(d / np.array(box))).max() < 1e-9
+            assert np.abs(qa[:n_owned, :3] - SL - q[ga[:n_owned], :3]).max() < 1e-12  # owned: shifted only
+            local = O.build_full(qa, SL, ext)  # open boundary over the extended box
+            return _rows(local, range(n_owned), ga), ga[:n_owned]
+
+        rows, gids = dec.build(None, torch.from_numpy(q_own), gid_owned=torch.from_numpy(gid_own), build_fn=build_fn)
+        want = _minimum_image_rows(q, box, gids)
+        assert len(rows) == len(want)
+        for a, b2 in zip(rows, want):
+            assert np.array_equal(a, b2)
+        cnt = dec.check()
+        assert len(cnt) == 6 and all(c > 0 for c in cnt)
+        tot = torch.tensor([q_own.shape[0]], dtype=torch.int64)
+        dist.all_reduce(tot)
+        assert int(tot) == q.shape[0]
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_periodic_ring_gives_minimum_image_rows(world):
+    from oracle import oracle as O
+    O.lib()
+    mp.spawn(_periodic_worker, args=(world, _free_port()), nprocs=world, join=True)
+
+
+def test_periodic_ring_preconditions():
+    from md_neighbor_list_b200.periodic import PeriodicSlabDecomposition
+    with pytest.raises(ValueError):
+        PeriodicSlabDecomposition(1, 0, (20.0, 20.0, 20.0), SL)          # one GPU: PeriodicVerletList
+    with pytest.raises(ValueError):
+        PeriodicSlabDecomposition(2, 0, (20.0, 6.0, 20.0), SL)           # an axis shorter than 2 SL
+    with pytest.raises(ValueError):
+        PeriodicSlabDecomposition(4, 0, (20.0, 20.0, 12.0), SL)          # slabs thinner than SL
