@@ -1,12 +1,14 @@
 // make_list_b200.cpp — a driver of the reference's shape (make_list.cu:102-201 for the GPU class, make_list.cpp:132-226
 // for the CPU classes) built on include/nlist_b200_shim.hpp: generate the jittered-FCC default system, build the list
 // LOOP times, print "# of particles N T[ms]", then verify against an O(N^2) brute force and print "TEST is passed."
-// usage: make_list_b200.out [gpu|cpu|md] [density] [loop] [check]
+// usage: make_list_b200.out [gpu|cpu|md|pbc] [density] [loop] [check]
 //   gpu : NeighListGPU interface (full list, list[k*N + i] layout)     cpu : NeighList interface (half list, CSR)
 //   md  : what the drivers' unused momenta `p` are for (make_list.cpp:135-140): LOOP velocity-Verlet steps of a
 //         Lennard-Jones system in a 20^3 box on the NeighListGPU interface — forces from the list on the device, the
 //         list rebuilt only when a particle has moved more than margin / 2 since the last build
 //         — then the forces of the (possibly several steps old) list are checked against an O(N^2) evaluation
+//   pbc : periodic boundaries (minimum image) on the NeighListPeriodicGPU shim class: FULL and HALF
+//         lists of a 20^3 box checked against an O(N^2) minimum-image brute force
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -144,9 +146,62 @@ int run_md(double density, int steps) {
   return 0;
 }
 
+int run_pbc(double density) {
+  const double Lp = 20.0;
+  const int64_t n64 = nlb200_workload_fcc(density, Lp, 0, 0, 0, 2, nullptr, 4, 0);
+  const int32_t N = (int32_t)n64;
+  nlb200::cuda_ptr<double4v> q;
+  q.allocate(N);
+  nlb200_workload_fcc(density, Lp, 0, 0, 0, 2, &q[0].x, 4, N);
+  q.host2dev();
+  const double sl2 = SEARCH_LENGTH * SEARCH_LENGTH;
+  // minimum-image brute force, rows ascending
+  std::vector<std::vector<int32_t>> rows(N);
+  for (int i = 0; i < N; i++)
+    for (int j = i + 1; j < N; j++) {
+      double d[3] = {q[j].x - q[i].x, q[j].y - q[i].y, q[j].z - q[i].z};
+      double r2 = 0.0;
+      for (int a = 0; a < 3; a++) {
+        d[a] -= Lp * std::nearbyint(d[a] / Lp);
+        r2 += d[a] * d[a];
+      }
+      if (r2 > sl2) continue;
+      rows[i].push_back(j);
+      rows[j].push_back(i);
+    }
+  for (int half = 0; half < 2; half++) {
+    nlb200::NeighListPeriodicGPU<double4v, double> nl(SEARCH_LENGTH, Lp, Lp, Lp, half != 0);
+    nl.Initialize(N);
+    nl.MakeNeighList(q, N, true);
+    nl.MakeNeighList(q, N, true);  // the second build replays the library's graph
+    const int64_t pairs = nl.number_of_pairs64();
+    auto& off = nl.offsets();
+    auto& list = nl.partners();
+    off.dev2host();
+    list.dev2host();
+    int64_t want_pairs = 0;
+    std::vector<int32_t> row;
+    for (int i = 0; i < N; i++) {
+      std::vector<int32_t> want;
+      for (int32_t j : rows[i])
+        if (!half || j > i) want.push_back(j);
+      std::sort(want.begin(), want.end());
+      want_pairs += (int64_t)want.size();
+      row.assign(&list[(std::size_t)off[i]], &list[(std::size_t)off[i]] + (off[i + 1] - off[i]));
+      std::sort(row.begin(), row.end());
+      if (row != want) return fail(half ? "pbc_half_row" : "pbc_full_row", i, (long long)row.size() - (long long)want.size());
+    }
+    if (pairs != want_pairs) return fail("pbc_pairs", pairs, want_pairs);
+    std::printf("# of particles %d periodic %s list: %lld entries\n", N, half ? "half" : "full", (long long)pairs);
+  }
+  std::fprintf(stderr, "TEST is passed.\n");
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
+  if (argc > 1 && std::strcmp(argv[1], "pbc") == 0) return run_pbc(argc > 2 ? std::atof(argv[2]) : 1.0);
   if (argc > 1 && std::strcmp(argv[1], "md") == 0)
     return run_md(argc > 2 ? std::atof(argv[2]) : 1.0, argc > 3 ? std::atoi(argv[3]) : 200);
   const bool gpu = argc < 2 || std::strcmp(argv[1], "cpu") != 0;

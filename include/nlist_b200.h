@@ -254,6 +254,12 @@ int nlb200_pack_slab2(const void* q_dev, const int32_t* gids_dev, int64_t n, int
 /* Bytes of workspace nlb200_select_slab / nlb200_pack_slab need for n particles. */
 int64_t nlb200_select_slab_workspace(int64_t n);
 
+/* f3 helper (periodic images): q[i][axis] += delta for i in [0, count) — an image is a copy of a
+ * particle shifted by one box length; absent (NaN) records stay absent.  The reference wraps cell indices only
+ * (neighlist_cpu.hpp:61-66) and measures plain distances (:219-223); minimum-image lists are built from the
+ * open-boundary build over image ghosts (nlb200_pack_slab2 + this + nlb200_build_subset). */
+int nlb200_shift_axis(void* q_dev, int64_t count, int dtype, int stride, int axis, double delta, void* stream);
+
 /* Gathers position records: dst[k] = src[idx[k]] (stride elements each). */
 int nlb200_gather_records(const void* src_dev, const int32_t* idx_dev, int64_t count, int dtype, int stride,
                           void* dst_dev, void* stream);

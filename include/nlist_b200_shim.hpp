@@ -215,6 +215,142 @@ class NeighListGPU {
   cuda_ptr<int32_t> list_, np_;
 };
 
+// Periodic boundaries (minimum image) with the NeighListGPU interface — SURVEY.md §8f f3.  The reference wraps cell
+// indices only (neighlist_cpu.hpp:61-66) and measures plain distances (:219-223); an MD caller needs the minimum image.
+// Every particle within the search length of a face gets an image beyond the opposite face, axis by axis (edge and
+// corner images are images of images); the images ride behind the particles as ghost records whose global id is the
+// imaged particle's id, and one open-boundary build over the box extended by the search length gives rows whose
+// partners are the minimum-image neighbours:
+//     q_all = [ particles | x images (lo, hi) | y images | z images ] + SL,   n_owned = N
+// Image buffers have a fixed capacity (absent slots are NaN records), so a build needs no host synchronisation.
+// Preconditions: positions in [0, L), L >= 2 * search_length per axis.  Output: CSR (offsets + partners), FULL or HALF.
+template <typename Vec, typename Dtype>
+class NeighListPeriodicGPU {
+ public:
+  NeighListPeriodicGPU(const Dtype search_length, const Dtype Lx, const Dtype Ly, const Dtype Lz,
+                       const bool half = false, const double slack = 1.5)
+      : sl_(search_length), slack_(slack) {
+    static_assert(sizeof(Vec) == 4 * sizeof(Dtype), "Vec must be {x, y, z, w} of Dtype");
+    L_[0] = Lx; L_[1] = Ly; L_[2] = Lz;
+    for (int a = 0; a < 3; a++)
+      if (L_[a] < 2.0 * sl_) die(nullptr, NLB200_ERR_INVALID, "NeighListPeriodicGPU: box shorter than 2 search lengths");
+    const int st = nlb200_create(sl_, Lx + 2 * sl_, Ly + 2 * sl_, Lz + 2 * sl_, dtype_code<Dtype>(),
+                                 half ? NLB200_HALF_CSR : NLB200_FULL_CSR, &h_);
+    if (st) die(nullptr, st, "NeighListPeriodicGPU");
+    half_ = half;
+    cuda_or_die(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+  }
+  ~NeighListPeriodicGPU() {
+    nlb200_destroy(h_);
+    if (stream_) cudaStreamDestroy(stream_);
+    if (ws_) cudaFree(ws_);
+    if (cnt_) cudaFree(cnt_);
+  }
+  NeighListPeriodicGPU(const NeighListPeriodicGPU&) = delete;
+  NeighListPeriodicGPU& operator=(const NeighListPeriodicGPU&) = delete;
+
+  void Initialize(const int32_t particle_number) {
+    n_ = particle_number;
+    int64_t cur = n_;
+    for (int a = 0; a < 3; a++) {
+      cap_[a] = ((int64_t)(cur * sl_ / L_[a] * slack_) + 256 + 31) / 32 * 32;
+      cur += 2 * cap_[a];
+    }
+    n_total_ = cur;
+    const double dens = n_ / (L_[0] * L_[1] * L_[2]);
+    const int64_t entries =
+        (int64_t)(n_ * dens * 4.18879 * sl_ * sl_ * sl_ * (half_ ? 0.5 : 1.0) * 1.3) + 16 * (int64_t)n_ + 1024;
+    check(nlb200_initialize(h_, n_total_, entries), "Initialize");
+    q_all_.allocate((std::size_t)n_total_);
+    gid_.allocate((std::size_t)n_total_);
+    for (int64_t i = 0; i < n_total_; i++) gid_[i] = i < n_ ? (int32_t)i : 0;
+    gid_.host2dev();
+    ws_bytes_ = 2 * nlb200_select_slab_workspace(n_total_) + 512;
+    cuda_or_die(cudaMalloc(&ws_, (std::size_t)ws_bytes_), "cudaMalloc");
+    cuda_or_die(cudaMalloc(reinterpret_cast<void**>(&cnt_), 6 * sizeof(int64_t)), "cudaMalloc");
+  }
+
+  void MakeNeighList(cuda_ptr<Vec>& q, const int32_t particle_number, const bool sync = true) {
+    if (particle_number != n_) die(h_, NLB200_ERR_INVALID, "MakeNeighList: particle number differs from Initialize");
+    enqueue(q.dev());
+    q_last_ = q.dev();
+    if (sync) synchronize();
+  }
+  void synchronize() {
+    for (int attempt = 0; attempt < 4; attempt++) {
+      const int st = nlb200_synchronize(h_);
+      if (st == NLB200_OK) break;
+      if (st == NLB200_ERR_CAPACITY) {
+        check(nlb200_reserve(h_, nlb200_required_entries(h_)), "reserve");
+      } else if (st == NLB200_ERR_CELL_CAPACITY) {
+        nlb200_stats s;
+        nlb200_get_stats(h_, &s);
+        check(nlb200_reserve_cell_capacity(h_, s.max_in_cell), "reserve_cell_capacity");
+      } else {
+        die(h_, st, "MakeNeighList");
+      }
+      if (attempt == 3) die(h_, NLB200_ERR_CAPACITY, "MakeNeighList");
+      enqueue(q_last_);
+    }
+    int64_t c[6];
+    cuda_or_die(cudaMemcpy(c, cnt_, sizeof(c), cudaMemcpyDeviceToHost), "image counts");
+    for (int a = 0; a < 3; a++)
+      if (c[2 * a] > cap_[a] || c[2 * a + 1] > cap_[a])
+        die(h_, NLB200_ERR_CAPACITY, "NeighListPeriodicGPU: more periodic images than the capacity, raise `slack`");
+  }
+  int64_t number_of_pairs64() {
+    synchronize();
+    return nlb200_number_of_pairs(h_);
+  }
+  cuda_ptr<int32_t>& number_of_partners() {
+    np_.borrow(nlb200_number_of_partners(h_), n_);
+    return np_;
+  }
+  cuda_ptr<int64_t>& offsets() {
+    off_.borrow(nlb200_offsets(h_), (std::size_t)n_ + 1);
+    return off_;
+  }
+  cuda_ptr<int32_t>& partners() {
+    list_.borrow(nlb200_partners(h_), (std::size_t)nlb200_number_of_pairs(h_));
+    return list_;
+  }
+
+ private:
+  void check(int st, const char* what) {
+    if (st) die(h_, st, what);
+  }
+  void enqueue(const void* q_dev) {
+    const int dt = dtype_code<Dtype>();
+    Dtype* qa = reinterpret_cast<Dtype*>(q_all_.dev());
+    cuda_or_die(cudaMemcpyAsync(qa, q_dev, sizeof(Vec) * (std::size_t)n_, cudaMemcpyDeviceToDevice, stream_), "copy");
+    int64_t cur = n_;
+    for (int a = 0; a < 3; a++) {
+      Dtype* lo = qa + 4 * cur;
+      Dtype* hi = qa + 4 * (cur + cap_[a]);
+      check(nlb200_pack_slab2(qa, gid_.dev(), cur, dt, 4, a, sl_, L_[a] - sl_, lo, gid_.dev() + cur, hi,
+                              gid_.dev() + cur + cap_[a], cap_[a], cnt_ + 2 * a, ws_, ws_bytes_, stream_),
+            "nlb200_pack_slab2");
+      check(nlb200_shift_axis(lo, cap_[a], dt, 4, a, L_[a], stream_), "nlb200_shift_axis");   // near the lower face: + L
+      check(nlb200_shift_axis(hi, cap_[a], dt, 4, a, -L_[a], stream_), "nlb200_shift_axis");
+      cur += 2 * cap_[a];
+    }
+    for (int a = 0; a < 3; a++) check(nlb200_shift_axis(qa, n_total_, dt, 4, a, sl_, stream_), "nlb200_shift_axis");
+    check(nlb200_build_subset(h_, qa, n_total_, n_, gid_.dev(), stream_), "MakeNeighList");
+  }
+  nlb200_handle h_ = nullptr;
+  cudaStream_t stream_ = nullptr;
+  double sl_, slack_, L_[3];
+  bool half_ = false;
+  int32_t n_ = 0;
+  int64_t n_total_ = 0, cap_[3] = {0, 0, 0}, ws_bytes_ = 0;
+  void* ws_ = nullptr;
+  int64_t* cnt_ = nullptr;
+  const void* q_last_ = nullptr;
+  cuda_ptr<Vec> q_all_;
+  cuda_ptr<int32_t> gid_, np_, list_;
+  cuda_ptr<int64_t> off_;
+};
+
 // neighlist_cpu.hpp:15-464 (and the AVX2 / AVX-512 classes, which share the interface): host positions in, half list
 // in CSR out, key = smaller index.  Vec may be {x,y,z} (scalar build, make_list.cpp:30) or {x,y,z,w} (make_list.cpp:28).
 template <typename Vec>

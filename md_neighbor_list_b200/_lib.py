@@ -65,6 +65,7 @@ SYMBOLS = {
     "nlb200_pack_slab2": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64,
                                     _vp]),
     "nlb200_select_slab_workspace": (_i64, [_i64]),
+    "nlb200_shift_axis": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _dbl, _vp]),
     "nlb200_gather_records": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "nlb200_workload_fcc": (_i64, [_dbl, _dbl, _i32, _i32, _i32, C.c_uint32, _vp, _i32, _i64]),
     "nlb200_workload_uniform": (_i64, [_i64, _dbl, C.c_uint64, _vp, _i32]),

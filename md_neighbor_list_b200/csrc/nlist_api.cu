@@ -1196,6 +1196,20 @@ int64_t nlb200_select_slab_workspace(int64_t n) {
   return (int64_t)(o_state + sizeof(unsigned long long) * (size_t)(tiles + 2));
 }
 
+int nlb200_shift_axis(void* q_dev, int64_t count, int dtype, int stride, int axis, double delta, void* stream) {
+  if (count < 0 || (stride != 3 && stride != 4) || axis < 0 || axis > 2 || (dtype != NLB200_F64 && dtype != NLB200_F32))
+    return NLB200_ERR_INVALID;
+  if (count == 0) return NLB200_OK;
+  if (!q_dev) return NLB200_ERR_INVALID;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned g = (unsigned)((count + 255) / 256);
+  if (dtype == NLB200_F64)
+    shift_axis_kernel<double><<<g, 256, 0, s>>>((double*)q_dev, count, stride, axis, delta);
+  else
+    shift_axis_kernel<float><<<g, 256, 0, s>>>((float*)q_dev, count, stride, axis, (float)delta);
+  return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
+}
+
 int nlb200_gather_records(const void* src_dev, const int32_t* idx_dev, int64_t count, int dtype, int stride,
                           void* dst_dev, void* stream) {
   if (count < 0 || (stride != 3 && stride != 4)) return NLB200_ERR_INVALID;

@@ -1605,6 +1605,15 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const T* __restrict_
   dst[t] = src[(int64_t)sorted_ids[slot] * width + c];
 }
 
+// f3 helper: q[i][axis] += delta for `count` records (periodic images are copies shifted by one box length; absent
+// NaN records stay NaN)
+template <typename T>
+__global__ void __launch_bounds__(256) shift_axis_kernel(T* __restrict__ q, int64_t count, int stride, int axis,
+                                                         T delta) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < count) q[i * stride + axis] += delta;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) gather_records_kernel(const T* __restrict__ src,
                                                              const int32_t* __restrict__ idx, int64_t count,

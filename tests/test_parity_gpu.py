@@ -591,6 +591,19 @@ def test_cpp_driver_md_loop(cuda):
     assert "list builds" in r.stdout
 
 
+def test_cpp_driver_periodic(cuda):
+    """drivers/make_list_b200.cpp pbc: minimum-image FULL and HALF lists on the C++ shim class NeighListPeriodicGPU
+    (nlb200_pack_slab2 + nlb200_shift_axis + nlb200_build_subset) against an O(N^2) minimum-image brute force."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "drivers", "make_list_b200.out")
+    if not os.path.exists(exe):
+        pytest.fail("drivers/make_list_b200.out is missing: run __graft_entry__.build()")
+    r = subprocess.run([exe, "pbc", "1.0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "TEST is passed." in r.stderr
+    assert "periodic full list" in r.stdout and "periodic half list" in r.stdout
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # callers either side of the build (SURVEY.md §8f f1, f2)
 # ---------------------------------------------------------------------------------------------------------------
