@@ -223,7 +223,7 @@ class NeighListGPU {
 // partners are the minimum-image neighbours:
 //     q_all = [ particles | x images (lo, hi) | y images | z images ] + SL,   n_owned = N
 // Image buffers have a fixed capacity (absent slots are NaN records), so a build needs no host synchronisation.
-// Preconditions: positions in [0, L), L >= 2 * search_length per axis.  Output: CSR (offsets + partners), FULL or HALF.
+// Preconditions: positions in [0, L), L > 2 * search_length per axis (strictly: L >= 2 SL (1 + 1e-9), checked).  Output: CSR (offsets + partners), FULL or HALF.
 template <typename Vec, typename Dtype>
 class NeighListPeriodicGPU {
  public:
@@ -233,7 +233,10 @@ class NeighListPeriodicGPU {
     static_assert(sizeof(Vec) == 4 * sizeof(Dtype), "Vec must be {x, y, z, w} of Dtype");
     L_[0] = Lx; L_[1] = Ly; L_[2] = Lz;
     for (int a = 0; a < 3; a++)
-      if (L_[a] < 2.0 * sl_) die(nullptr, NLB200_ERR_INVALID, "NeighListPeriodicGPU: box shorter than 2 search lengths");
+      // strictly longer than two search lengths (same margin as the Python classes, periodic.py): at L == 2 SL a pair
+      // at r == SL and its image at L - r == SL would both pass `!(r2 > SL2)` and row i would list j twice
+      if (!(L_[a] >= 2.0 * sl_ * (1.0 + 1e-9)))
+        die(nullptr, NLB200_ERR_INVALID, "NeighListPeriodicGPU: every box edge must exceed 2 search lengths");
     const int st = nlb200_create(sl_, Lx + 2 * sl_, Ly + 2 * sl_, Lz + 2 * sl_, dtype_code<Dtype>(),
                                  half ? NLB200_HALF_CSR : NLB200_FULL_CSR, &h_);
     if (st) die(nullptr, st, "NeighListPeriodicGPU");

@@ -75,6 +75,7 @@ struct nlb200_context {
   cudaStream_t last_stream = nullptr;
   bool build_pending = false;
   bool have_result = false;
+  bool have_build = false;  // some build has been enqueued since initialize (nlb200_mark_enqueued needs one)
   int64_t last_n = 0, last_owned = 0;
   nlb200_stats stats{};
 
@@ -543,15 +544,34 @@ int64_t estimate_entries(const nlb200_context* h, int64_t n) {
   return (int64_t)e;
 }
 
+// New buffer first, old one released only on success: a failed growth (the masks cost 108 * ceil(max_in_cell / 32)
+// bytes per particle, so one dense cell of a clustered input can ask for more than the device has) leaves the handle
+// exactly as it was — same buffers, same capacities — instead of initialized with a null pointer.
 int alloc_mask(nlb200_context* h, int64_t max_in_cell) {
-  if (h->mask) cudaFree(h->mask);
-  h->mask = nullptr;
   int64_t wi = (max_in_cell + 31) / 32;
   if (wi < 1) wi = 1;
+  const int64_t ncap = (int64_t)align_up((size_t)(h->max_n > 0 ? h->max_n : 1), 32);
+  uint32_t* fresh = nullptr;
+  CK(h, cudaMalloc(&fresh, sizeof(uint32_t) * (size_t)(27 * wi * ncap)));
+  if (h->mask) cudaFree(h->mask);
+  h->mask = fresh;
   h->mask_wi = (int32_t)wi;
-  h->mask_ncap = (int64_t)align_up((size_t)(h->max_n > 0 ? h->max_n : 1), 32);
-  CK(h, cudaMalloc(&h->mask, sizeof(uint32_t) * (size_t)(27 * wi * h->mask_ncap)));
+  h->mask_ncap = ncap;
   return NLB200_OK;
+}
+
+// Before an output buffer is replaced: wait for the build that may still write it, and forget that build — its
+// status word must not be reported again by a later nlb200_synchronize over the new, empty buffers.
+cudaError_t settle_before_realloc(nlb200_context* h) {
+  if (h->build_pending) {
+    const cudaError_t e = cudaStreamSynchronize(h->last_stream);
+    if (e != cudaSuccess) return e;
+  }
+  h->build_pending = false;
+  h->have_result = false;
+  if (h->status_host) h->status_host->flags = 0;
+  drop_graph(h);
+  return cudaSuccess;
 }
 
 int64_t estimate_max_in_cell(const nlb200_context* h, int64_t n) {
@@ -565,9 +585,10 @@ int64_t estimate_max_in_cell(const nlb200_context* h, int64_t n) {
 }
 
 int alloc_partners(nlb200_context* h, int64_t entries) {
+  int32_t* fresh = nullptr;
+  CK(h, cudaMalloc(&fresh, sizeof(int32_t) * (size_t)(entries > 0 ? entries : 1)));
   if (h->partners) cudaFree(h->partners);
-  h->partners = nullptr;
-  CK(h, cudaMalloc(&h->partners, sizeof(int32_t) * (size_t)(entries > 0 ? entries : 1)));
+  h->partners = fresh;
   h->cap_entries = entries;
   return NLB200_OK;
 }
@@ -720,24 +741,21 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
   h->initialized = true;
   h->have_result = false;
   h->build_pending = false;
+  h->have_build = false;
   return NLB200_OK;
 }
 
 int nlb200_reserve(nlb200_handle h, int64_t max_entries) {
   if (!h || !h->initialized) return h ? fail(h, NLB200_ERR_STATE, "reserve before initialize") : NLB200_ERR_INVALID;
   if (max_entries <= h->cap_entries) return NLB200_OK;
-  if (h->build_pending) CK(h, cudaStreamSynchronize(h->last_stream));
-  drop_graph(h);
-  h->have_result = false;
+  CK(h, settle_before_realloc(h));
   return alloc_partners(h, max_entries);
 }
 
 int nlb200_reserve_cell_capacity(nlb200_handle h, int64_t max_in_cell) {
   if (!h || !h->initialized) return h ? fail(h, NLB200_ERR_STATE, "reserve before initialize") : NLB200_ERR_INVALID;
   if (max_in_cell <= (int64_t)h->mask_wi * 32) return NLB200_OK;
-  if (h->build_pending) CK(h, cudaStreamSynchronize(h->last_stream));
-  drop_graph(h);
-  h->have_result = false;
+  CK(h, settle_before_realloc(h));
   return alloc_mask(h, max_in_cell);
 }
 
@@ -818,12 +836,13 @@ int nlb200_build_subset(nlb200_handle h, const void* q_dev, int64_t n_total, int
   h->have_result = false;
   h->last_n = n_total;
   h->last_owned = n_owned;
+  h->have_build = true;
   return NLB200_OK;
 }
 
 int nlb200_mark_enqueued(nlb200_handle h, void* stream) {
   if (!h) return NLB200_ERR_INVALID;
-  if (!h->initialized || h->last_n < 0) return fail(h, NLB200_ERR_STATE, "no build to mark");
+  if (!h->initialized || !h->have_build) return fail(h, NLB200_ERR_STATE, "no build to mark");
   h->last_stream = reinterpret_cast<cudaStream_t>(stream);
   h->build_pending = true;
   h->have_result = false;

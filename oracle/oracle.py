@@ -255,13 +255,15 @@ def ref_available(variant: str) -> bool:
 _ref_libs: dict = {}
 
 
-def ref_build(variant: str, q: np.ndarray, sl: float, box, loops: int = 1):
-    """Run the reference class `variant` on q (n x 4 float64).  Returns (CSR with int64 offsets, ms_per_build)."""
+def ref_build(variant: str, q: np.ndarray, sl: float, box, loops: int = 1, warmup: int = 0):
+    """Run the reference class `variant` on q (n x 4 float64): `warmup` untimed builds, then `loops` timed ones on the
+    same instance (the reference's own protocol, make_list.cpp:152-157).  Returns (CSR with int64 offsets,
+    ms_per_build)."""
     if variant not in _ref_libs:
         L = C.CDLL(os.path.join(REF_DIR, REF_VARIANTS[variant]))
-        L.ref_build.restype = C.c_int
-        L.ref_build.argtypes = [_vp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32,
-                                _vp, _vp, _vp, C.c_int64, _i64p, C.POINTER(C.c_double)]
+        L.ref_build_warm.restype = C.c_int
+        L.ref_build_warm.argtypes = [_vp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32,
+                                     C.c_int32, _vp, _vp, _vp, C.c_int64, _i64p, C.POINTER(C.c_double)]
         L.ref_pair_capacity.restype = C.c_int64
         L.ref_pair_capacity.argtypes = [C.c_int64]
         _ref_libs[variant] = L
@@ -275,8 +277,8 @@ def ref_build(variant: str, q: np.ndarray, sl: float, box, loops: int = 1):
     lst = np.zeros(cap, dtype=np.int32)
     npairs = C.c_int64(0)
     ms = C.c_double(0)
-    rc = L.ref_build(_ptr(q), n, sl, box[0], box[1], box[2], loops, _ptr(np_), _ptr(kp), _ptr(lst), cap,
-                     C.byref(npairs), C.byref(ms))
+    rc = L.ref_build_warm(_ptr(q), n, sl, box[0], box[1], box[2], warmup, loops, _ptr(np_), _ptr(kp), _ptr(lst),
+                          cap, C.byref(npairs), C.byref(ms))
     if rc:
         raise RuntimeError(f"reference {variant} failed: {rc}")
     return CSR(np_, kp.astype(np.int64), lst[: npairs.value].copy()), ms.value

@@ -59,6 +59,27 @@ def sort_rows(oracle, lst, off):
     return out
 
 
+def open_stencil_tests(mesh_index, mesh):
+    """sum over cells A of n_A * (particles in the stencil of A), stencil = [c-1, c+1] clamped to the box per axis
+    (all three cells on a 3-cell axis, where the reference's wrapped cell is a real neighbour)."""
+    cnt = np.diff(mesh_index).reshape(mesh[2], mesh[1], mesh[0]).astype(np.int64)
+    win = cnt
+    for ax, m in ((0, mesh[2]), (1, mesh[1]), (2, mesh[0])):
+        if m == 3:
+            win = np.broadcast_to(win.sum(axis=ax, keepdims=True), win.shape).copy()
+        else:
+            pad = [(0, 0)] * 3
+            pad[ax] = (1, 1)
+            p = np.pad(win, pad)
+            sl = [slice(None)] * 3
+            acc = np.zeros_like(win)
+            for o in range(3):
+                sl[ax] = slice(o, o + m)
+                acc = acc + p[tuple(sl)]
+            win = acc
+    return int((cnt * win).sum())
+
+
 def assert_matches(oracle, got, ref):
     """ref: oracle CSR (any row order).  Bit-exact after the per-row sort the reference tests apply
     (make_list.cpp:120-128,205-220)."""
@@ -101,7 +122,12 @@ def test_default_system_full_matches_oracle(cuda, oracle, dens):
     q = workloads.fcc(dens)
     got = gpu_build(cuda, q, 3.3, BOX50, "full_csr", builds=3)
     assert got["pairs"] == g["full"]["number_of_pairs"]
-    assert got["candidates"] == g["full"]["candidates_27"] or got["candidates"] <= g["full"]["candidates_27"]
+    # distance tests evaluated by one pass: every ordered pair of the open-boundary stencil (the wrapped stencil cells
+    # of the reference's 27, neighlist_gpu.hpp:125-142, can never pass the non-periodic distance test on a >= 4-cell
+    # axis and are skipped) — pinned exactly, from the oracle's cell table
+    assert got["candidates"] == open_stencil_tests(oracle.bin_particles(q, 3.3, BOX50, gpu_clamp=True)[0],
+                                                   oracle.mesh_dims(3.3, BOX50))
+    assert got["candidates"] <= g["full"]["candidates_27"]
     assert oracle.fnv1a64(sort_rows(oracle, got["list"], got["off"])) == g["full"]["list_rowsorted_fnv"]
     assert oracle.fnv1a64(got["off"]) == g["full"]["offsets_i64_fnv"]
     assert got["max_partners"] == g["full"]["max_partners"]
@@ -453,17 +479,24 @@ def test_absent_ghost_slots_and_halo_packing(cuda, oracle):
 # full-size properties (BASELINE.json configs[2]: 16M uniform, density 1.0, SL 3.3)
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [1 << 21, 1 << 24])
-def test_large_uniform_properties(cuda, n):
-    """Size-independent properties at sizes no CPU oracle finishes quickly: CSR consistency, FULL = HALF mirrored
+def test_large_uniform_properties(cuda, oracle, n):
+    """configs[2] at sizes the reference itself cannot check (fixed capacities, O(N^2) self-test: SURVEY.md §8c).
+    Pinned three ways: (1) FNV-1a digests of the oracle's HALF list (counts, offsets, row-sorted partners) and FULL
+    counts, generated in the build container by tests/golden/make_golden_uniform.py; (2) at 2^21 the oracle is re-run
+    here and compared element by element; (3) size-independent properties: CSR consistency, FULL = HALF mirrored
     (count_full[i] = count_half[i] + #times i is a partner in HALF), checksum of checksums, no self pairs."""
     from md_neighbor_list_b200 import VerletListB200, workloads
     torch = cuda
     L = float(round(n ** (1.0 / 3.0)))  # density ~1.0 (2^24 -> 256)
     q = workloads.uniform(n, L)
+    with open(os.path.join(GOLD, "uniform_large.json")) as f:
+        gold = json.load(f)[f"n_{n}"]
+    assert oracle.fnv1a64(q[:, :3]) == gold["positions_xyz_fnv"]  # same generator on this host
     qd = torch.from_numpy(q).cuda()
     res = {}
     for mode in ("half_csr", "full_csr"):
-        nl = VerletListB200(3.3, L, L, L, mode=mode)
+        # HALF rows are sorted on the device so that the list can be digested as the oracle's row-sorted list
+        nl = VerletListB200(3.3, L, L, L, mode=mode, sort_rows=(mode == "half_csr"))
         nl.initialize(n)
         nl.build(qd)
         st = nl.synchronize()
@@ -471,12 +504,25 @@ def test_large_uniform_properties(cuda, n):
         assert int(off[-1]) == st.number_of_pairs == int(cnt.sum(dtype=torch.int64))
         assert bool((off[1:] - off[:-1] == cnt).all())
         assert int(lst.min()) >= 0 and int(lst.max()) < n
+        assert st.number_of_pairs == gold[mode[:4]]["number_of_pairs"]
+        assert st.max_partners == gold[mode[:4]]["max_partners"]
+        assert oracle.fnv1a64(cnt.cpu().numpy()) == gold[mode[:4]]["number_of_partners_fnv"]
         rows = torch.repeat_interleave(torch.arange(n, device=lst.device, dtype=torch.int32), cnt.long())
         if mode == "half_csr":
             assert bool((lst > rows).all())
             res["half_cnt"] = cnt.clone()
             res["half_in"] = torch.bincount(lst.long(), minlength=n)
             res["half_pairs"] = st.number_of_pairs
+            off_h = off.cpu().numpy()
+            assert oracle.fnv1a64(off_h) == gold["half"]["offsets_i64_fnv"]
+            lst_h = lst.cpu().numpy()
+            assert oracle.fnv1a64(lst_h) == gold["half"]["list_rowsorted_fnv"]
+            if n <= (1 << 21):
+                ref = oracle.build_half(q, 3.3, (L, L, L)).sorted_rows()
+                assert np.array_equal(off_h, ref.offsets) and np.array_equal(lst_h, ref.partners)
+                assert np.array_equal(cnt.cpu().numpy(), ref.number_of_partners)
+                del ref
+            del lst_h, off_h
         else:
             assert bool((lst != rows).all())
             assert st.number_of_pairs == 2 * res["half_pairs"]
@@ -491,6 +537,36 @@ def test_large_uniform_properties(cuda, n):
         del rows
         nl.close()
         torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: cutoff sweep rc 2.0-4.5 (+0.3 margin) x density 0.5/1.0 on clustered particles
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dens", [0.5, 1.0])
+def test_cutoff_sweep_on_clustered_particles(cuda, oracle, dens):
+    """List-length and load-imbalance stress (SURVEY.md §8d C4 at 2^16 particles): half of the particles sit in 32
+    Gaussian blobs, so cells hold from a handful to > 1000 particles and rows from ~10 to > 2000 partners.  Every rc of
+    the sweep is compared with the oracle element by element (FULL), the ends of the sweep also as HALF lists."""
+    from md_neighbor_list_b200 import workloads
+    n = 1 << 16
+    L = (n / dens) ** (1.0 / 3.0)
+    box = (L, L, L)
+    q = workloads.clustered(n, L)
+    seen_max_cell = 0
+    for rc in (2.0, 2.5, 3.0, 3.5, 4.0, 4.5):
+        sl = rc + 0.3
+        got = gpu_build(cuda, q, sl, box, "full_csr")
+        ref = oracle.build_full(q, sl, box)
+        assert_matches(oracle, got, ref)
+        assert got["max_partners"] == int(ref.number_of_partners.max())
+        seen_max_cell = max(seen_max_cell, got["max_in_cell"])
+        got["handle"].close()
+        if rc in (2.0, 4.5):
+            got = gpu_build(cuda, q, sl, box, "half_csr")
+            assert_matches(oracle, got, oracle.build_half(q, sl, box))
+            got["handle"].close()
+        cuda.cuda.empty_cache()
+    assert seen_max_cell > 1000
 
 
 # ---------------------------------------------------------------------------------------------------------------
