@@ -15,6 +15,7 @@
 
 #include "../../include/nlist_b200.h"
 #include "nlist_kernels.cuh"
+#include "nlist_rowmask.cuh"
 
 using namespace nlb;
 
@@ -54,6 +55,12 @@ struct nlb200_context {
   uint32_t* mask = nullptr;  // [27][mask_wi][mask_ncap] pair-mask words
   int32_t mask_wi = 0;       // words per (row, stencil cell): cells may hold up to 32*mask_wi particles
   int64_t mask_ncap = 0;
+  CellRec* cellrec = nullptr;    // [M] per-cell records of the row-mask path
+  uint32_t* rmask = nullptr;     // row-mask words (per-cell blocks handed out by a cursor)
+  int64_t rmask_cap = 0;         // ... capacity in words
+  int64_t rmask_need = 0;        // words the last synchronized build asked for
+  int32_t win_cap = 0;           // candidates staged per window round
+  float band_v3 = 0.f;           // pre-filter band of the row-mask path (absolute FP32 records)
   bool pdl = false;             // NLB200_OPT_PDL
   int64_t max_in_cell_opt = 0;  // NLB200_OPT_MAX_IN_CELL (0 = estimate from the density)
   int32_t* counts = nullptr;
@@ -95,10 +102,10 @@ struct nlb200_context {
 };
 
 enum StageId { ST_ZERO = 0, ST_BIN, ST_SCAN_CELLS, ST_SCATTER, ST_CELLSORT, ST_COUNT, ST_SCAN_COUNTS, ST_FILL,
-               ST_SORT_ROWS, ST_ELL, ST_STATUS, ST_PAIRMASK, ST_ROWCOUNT, ST_EMIT, ST_NUM };
+               ST_SORT_ROWS, ST_ELL, ST_STATUS, ST_PAIRMASK, ST_ROWCOUNT, ST_EMIT, ST_ROWMASK, ST_EMIT3, ST_NUM };
 static const char* const kStageNames[ST_NUM] = {"zero", "bin", "scan_cells", "scatter", "cellsort", "search_count",
                                                 "scan_counts", "search_fill", "sort_rows", "ell", "status_copy",
-                                                "pairmask", "row_count", "emit"};
+                                                "pairmask", "row_count", "emit", "rowmask", "emit3"};
 
 namespace {
 
@@ -165,6 +172,8 @@ void free_buffers(nlb200_context* h) {
   F(h->slot_cell);
   F(h->slot_gid);
   F(h->mask);
+  F(h->rmask);
+  F(h->cellrec);
   F(h->rec);
   F(h->counts);
   F(h->offsets);
@@ -313,6 +322,56 @@ cudaError_t launch_search(bool half, bool fill, bool exact, const SearchArgs<T>&
               : launch_search_e<T, STRIDE, false, false>(exact, a, grid, block, smem, s);
 }
 
+
+// Which search/emission pair a handle runs (NLB200_OPT_KERNEL_VARIANT):
+//   0 (default), 5: row masks      — rowmask_kernel + emit3_kernel (nlist_rowmask.cuh)
+//   1, or NLB200_OPT_EXACT_ONLY:   — search_kernel twice (count, fill): every test in the input precision if asked
+//   2, 3, 4, 7, 100..:             — round-1 pair masks (pairmask_kernel, rowcount_kernel, emit_kernel) and its ablations
+bool uses_v1(const nlb200_context* h) { return h->exact_only != 0 || h->variant == 1; }
+bool uses_rowmask(const nlb200_context* h) {
+  return !uses_v1(h) && (h->variant == 0 || h->variant == 5);
+}
+
+template <typename T, int STRIDE, int HALFMODE>
+cudaError_t set_rm_attr_h() {
+  return cudaFuncSetAttribute(rowmask_kernel<T, STRIDE, HALFMODE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              MAX_EMIT_SMEM);
+}
+template <typename T, int STRIDE>
+cudaError_t set_rm_attr() {
+  cudaError_t e;
+  if ((e = set_rm_attr_h<T, STRIDE, 0>()) != cudaSuccess) return e;
+  if ((e = set_rm_attr_h<T, STRIDE, 1>()) != cudaSuccess) return e;
+  return set_rm_attr_h<T, STRIDE, 2>();
+}
+cudaError_t set_rowmask_attrs() {
+  cudaError_t e;
+  if ((e = set_rm_attr<double, 4>()) != cudaSuccess) return e;
+  if ((e = set_rm_attr<double, 3>()) != cudaSuccess) return e;
+  if ((e = set_rm_attr<float, 4>()) != cudaSuccess) return e;
+  if ((e = set_rm_attr<float, 3>()) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(emit3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM);
+}
+
+template <typename T, int STRIDE, int HALFMODE>
+int launch_rowmask_h(nlb200_context* h, const RowMaskArgs<T>& a, cudaStream_t s) {
+  const size_t smem = rm_smem_bytes(a.win_cap);
+  int per_sm = 0;
+  CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rowmask_kernel<T, STRIDE, HALFMODE, 8>, RM_THREADS,
+                                                      smem));
+  if (per_sm < 1) return fail(h, NLB200_ERR_CUDA, "row-mask kernel does not fit an SM (%zu bytes of shared memory)", smem);
+  int64_t grid = (int64_t)per_sm * h->sm_count;
+  if (grid > a.gp.n_cells) grid = a.gp.n_cells;
+  CK(h, launch_chain(rowmask_kernel<T, STRIDE, HALFMODE, 8>, dim3((unsigned)grid), dim3(RM_THREADS), smem, s, a));
+  return NLB200_OK;
+}
+template <typename T, int STRIDE>
+int launch_rowmask(nlb200_context* h, int halfmode, const RowMaskArgs<T>& a, cudaStream_t s) {
+  if (halfmode == 0) return launch_rowmask_h<T, STRIDE, 0>(h, a, s);
+  if (halfmode == 1) return launch_rowmask_h<T, STRIDE, 1>(h, a, s);
+  return launch_rowmask_h<T, STRIDE, 2>(h, a, s);
+}
+
 template <typename T>
 const GridParams<T>& grid_of(const nlb200_context* h);
 template <>
@@ -368,13 +427,70 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     CK(h, stage(ST_CELLSORT));
     int64_t cs_blocks = ((int64_t)M * 32 + 127) / 128;
     if (cs_blocks > (int64_t)h->sm_count * 64) cs_blocks = (int64_t)h->sm_count * 64;  // warps stride over the cells
-    CK(h, launch_chain(cellsort_kernel<T, STRIDE>, dim3((unsigned)cs_blocks), dim3(128), 0, s, q, gp,
-                       (const int32_t*)h->cell_start, (const int32_t*)h->perm, h->sorted_ids, h->rec, h->slot_cell,
-                       gids, h->slot_gid));
+    if (uses_rowmask(h))
+      CK(h, launch_chain(cellsort_kernel<T, STRIDE, true>, dim3((unsigned)cs_blocks), dim3(128), 0, s, q, gp,
+                         (const int32_t*)h->cell_start, (const int32_t*)h->perm, h->sorted_ids, h->rec, h->slot_cell,
+                         gids, h->slot_gid));
+    else
+      CK(h, launch_chain(cellsort_kernel<T, STRIDE, false>, dim3((unsigned)cs_blocks), dim3(128), 0, s, q, gp,
+                         (const int32_t*)h->cell_start, (const int32_t*)h->perm, h->sorted_ids, h->rec, h->slot_cell,
+                         gids, h->slot_gid));
   }
   const bool half = h->mode == NLB200_HALF_CSR;
-  const bool use_v1 = h->exact_only != 0 || h->variant == 1;
-  if (use_v1) {
+  const bool use_v1 = uses_v1(h);
+  if (uses_rowmask(h)) {
+    // --- default: row masks.  Search (every test once, verdict blocks transposed to row-major words, row lengths
+    //     on the way) -> offsets -> emission. ---
+    RowMaskArgs<T> rm;
+    rm.q = q;
+    rm.gp = gp;
+    rm.cell_start = h->cell_start;
+    rm.rec = h->rec;
+    rm.global_ids = gids;
+    rm.n_owned = (int32_t)n_owned;
+    rm.mask = h->rmask;
+    rm.mask_cap = (unsigned long long)h->rmask_cap;
+    rm.cellrec = h->cellrec;
+    rm.counts = h->counts;
+    rm.d_mx = make_fastdiv((uint32_t)gp.mesh[0]);
+    rm.d_my = make_fastdiv((uint32_t)gp.mesh[1]);
+    rm.band = h->band_v3;
+    rm.win_cap = h->win_cap;
+    rm.queue = h->queue;
+    rm.st = h->status_dev;
+    CK(h, stage(ST_ROWMASK));
+    if (n > 0) {
+      const int rc = launch_rowmask<T, STRIDE>(h, !half ? 0 : (gids == nullptr ? 1 : 2), rm, s);
+      if (rc) return rc;
+    }
+    CK(h, stage(ST_SCAN_COUNTS));
+    {
+      const int tiles = (int)((n_owned + SCAN_TILE - 1) / SCAN_TILE);
+      CK(h, launch_chain(scan_kernel<int64_t>, dim3(tiles > 0 ? tiles : 1), dim3(SCAN_THREADS), 0, s,
+                         (const int32_t*)h->counts, (int64_t)n_owned, h->offsets, h->offsets32, h->scan_state_counts,
+                         h->status_dev, &h->status_dev->max_partners, (long long)h->cap_entries));
+    }
+    CK(h, stage(ST_EMIT3));
+    if (n > 0) {
+      Emit3Args em;
+      em.cell_start = h->cell_start;
+      em.sorted_ids = h->sorted_ids;
+      em.slot_cell = h->slot_cell;
+      em.slot_pid = gids != nullptr ? h->slot_gid : h->sorted_ids;
+      em.cellrec = h->cellrec;
+      em.mask = h->rmask;
+      em.n_total = n;
+      em.n_owned = (int32_t)n_owned;
+      em.n_cells = M;
+      em.offsets = h->offsets;
+      em.partners = h->partners;
+      em.capacity = h->cap_entries;
+      em.st = h->status_dev;
+      constexpr int rows = EM3_WARPS * 32;
+      CK(h, launch_chain(emit3_kernel, dim3((unsigned)((n + rows - 1) / rows)), dim3(rows),
+                         (size_t)rows * EM_LINE * sizeof(int32_t), s, em));
+    }
+  } else if (use_v1) {
     // --- v1: one CTA per cell, thread per particle, test evaluated twice (count, fill).  Kept for the exact-only
     //     validation mode and as an ablation. ---
     const double avg = (double)n_total / (double)M;
@@ -574,6 +690,15 @@ cudaError_t settle_before_realloc(nlb200_context* h) {
   return cudaSuccess;
 }
 
+int alloc_rmask(nlb200_context* h, int64_t words) {
+  uint32_t* fresh = nullptr;
+  CK(h, cudaMalloc(&fresh, sizeof(uint32_t) * (size_t)(words > 0 ? words : 1)));
+  if (h->rmask) cudaFree(h->rmask);
+  h->rmask = fresh;
+  h->rmask_cap = words;
+  return NLB200_OK;
+}
+
 int64_t estimate_max_in_cell(const nlb200_context* h, int64_t n) {
   // mean occupancy + 6 sigma of a Poisson cell count + slack; lattices stay well below (13-63 at
   // mean 35.3).  Floor of 80 (3 words): a rank of a slab decomposition bins on the GLOBAL grid, so n / cells
@@ -677,6 +802,7 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
     return fail(h, NLB200_ERR_CUDA, "no CUDA device: libnlist_b200 has no CPU fallback");
   CK(h, cudaGetDevice(&h->device));
   CK(h, set_search_attrs());
+  CK(h, set_rowmask_attrs());
   free_buffers(h);
   const int64_t n = max_particles > 0 ? max_particles : 1;
   const int64_t M = h->n_cells;
@@ -723,8 +849,39 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
   const int64_t entries = max_entries > 0 ? max_entries : estimate_entries(h, n);
   int rc = alloc_partners(h, entries);
   if (rc) return rc;
-  rc = alloc_mask(h, h->max_in_cell_opt > 0 ? h->max_in_cell_opt : estimate_max_in_cell(h, n));
-  if (rc) return rc;
+  {
+    const int64_t mic = h->max_in_cell_opt > 0 ? h->max_in_cell_opt : estimate_max_in_cell(h, n);
+    if (uses_rowmask(h)) {
+      CK(h, cudaMalloc(&h->cellrec, sizeof(CellRec) * (size_t)M));
+      // one bit per test: rows x ceil(27 cells x mic / 32) words is a bound for a uniform density; clustered inputs
+      // report NLB200_ERR_CELL_CAPACITY with the exact need and nlb200_reserve_cell_capacity grows the buffer
+      const int64_t per_row = (27 * mic + 31) / 32 + 1;
+      rc = alloc_rmask(h, n * per_row + 4096);
+      if (rc) return rc;
+      // window round: ~1.2 x the mean window, in chunks of 256 candidates (8 per lane), 512..6144
+      const double avg = (double)n / (double)M;
+      int64_t wc = (int64_t)(27.0 * (avg > 1.0 ? avg : 1.0) * 1.2);
+      wc = (wc + 255) / 256 * 256;
+      if (wc < 512) wc = 512;
+      if (wc > 6144) wc = 6144;
+      h->win_cap = (int32_t)wc;
+      // band of the FP32 pre-filter for absolute FP32 records: the evaluation error in the cell frame (384 u ms^2,
+      // DESIGN.md §6) plus what the rounding of both particles' coordinates to FP32 can move (SL^2 - r^2)/2 inside
+      // r < 2 SL: 2 SL * 2 sqrt(3) * ulp(max |coordinate|)/2 < 8 SL * eps_abs
+      double lmax = 0, msmax = 0;
+      for (int d = 0; d < 3; d++) {
+        lmax = std::max(lmax, h->L[d]);
+        msmax = std::max(msmax, h->L[d] / (double)h->mesh[d]);
+      }
+      int ex = 0;
+      std::frexp(lmax + 2.0 * msmax, &ex);  // value < 2^ex: ulp = 2^(ex - 24)
+      const double eps_abs = h->dtype == NLB200_F64 ? std::ldexp(1.0, ex - 25) : 0.0;
+      h->band_v3 = (float)(384.0 * std::ldexp(1.0, -24) * msmax * msmax + 8.0 * h->sl * eps_abs);
+    } else if (!uses_v1(h)) {
+      rc = alloc_mask(h, mic);
+      if (rc) return rc;
+    }
+  }
   if (h->mode == NLB200_FULL_ELL_TRANSPOSED) {
     // neighlist_gpu.hpp:102,271-274: MAX_PARTNERS * N ints, filled with -1 once
     const int64_t tot = (int64_t)h->ell_rows * n;
@@ -754,7 +911,14 @@ int nlb200_reserve(nlb200_handle h, int64_t max_entries) {
 
 int nlb200_reserve_cell_capacity(nlb200_handle h, int64_t max_in_cell) {
   if (!h || !h->initialized) return h ? fail(h, NLB200_ERR_STATE, "reserve before initialize") : NLB200_ERR_INVALID;
-  if (max_in_cell <= (int64_t)h->mask_wi * 32) return NLB200_OK;
+  if (uses_rowmask(h)) {
+    // the row-mask buffer holds one bit per test: grow it to what the failed build asked for (+ 1/16)
+    const int64_t need = h->rmask_need + h->rmask_need / 16 + 4096;
+    if (need <= h->rmask_cap) return NLB200_OK;
+    CK(h, settle_before_realloc(h));
+    return alloc_rmask(h, need);
+  }
+  if (uses_v1(h) || max_in_cell <= (int64_t)h->mask_wi * 32) return NLB200_OK;
   CK(h, settle_before_realloc(h));
   return alloc_mask(h, max_in_cell);
 }
@@ -871,9 +1035,13 @@ int nlb200_synchronize(nlb200_handle h) {
   for (int d = 0; d < 3; d++) h->stats.mesh[d] = h->mesh[d];
   h->stats.max_partners = st.max_partners;
   h->stats.max_in_cell = st.max_in_cell;
+  h->rmask_need = (int64_t)st.mask_words;
   h->have_result = true;
   if (st.flags & FLAG_OUT_OF_BOX)
     return fail(h, NLB200_ERR_OUT_OF_BOX, "a particle lies more than one cell outside [0,L] or is NaN");
+  if (st.flags & FLAG_MASK_WORDS)
+    return fail(h, NLB200_ERR_CELL_CAPACITY, "the row masks need %lld words, the buffer holds %lld (most crowded cell: %d)",
+                (long long)st.mask_words, (long long)h->rmask_cap, st.max_in_cell);
   if (st.flags & FLAG_CELL_WORDS)
     return fail(h, NLB200_ERR_CELL_CAPACITY, "a cell holds %d particles, the pair-mask words cover %d", st.max_in_cell,
                 h->mask_wi * 32);

@@ -51,6 +51,7 @@ struct DeviceStatus {
   int32_t max_partners;
   int32_t max_in_cell;
   int32_t pad;
+  unsigned long long mask_words;  // row-mask words requested by the cells (cursor of the per-cell blocks)
 };
 
 template <typename T>
@@ -346,7 +347,10 @@ __global__ void __launch_bounds__(256) scatter_kernel(const int2* __restrict__ c
 //    sorted_ids[slot] = id, slot_cell[slot] = cell
 //    One warp per cell; rank sort with warp shuffles (O(n^2/32) per cell, n ~ 35).
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int STRIDE>
+// ABS: records hold the ABSOLUTE coordinates rounded to FP32 (the row-mask search shifts them into a cell frame with
+// three subtractions; its band E accounts for the rounding, nlist_api.cu), else coordinates relative to the
+// particle's own cell corner (round-1 search kernels).
+template <typename T, int STRIDE, bool ABS>
 __global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, GridParams<T> gp,
                                                        const int32_t* __restrict__ cell_start,
                                                        const int32_t* __restrict__ perm,
@@ -380,9 +384,9 @@ __global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, 
     if (valid) {
       const Vec3<T> p = load_pos<T, STRIDE>(q, id);
       float4 r;
-      r.x = (float)((double)p.x - ox);
-      r.y = (float)((double)p.y - oy);
-      r.z = (float)((double)p.z - oz);
+      r.x = ABS ? (float)p.x : (float)((double)p.x - ox);
+      r.y = ABS ? (float)p.y : (float)((double)p.y - oy);
+      r.z = ABS ? (float)p.z : (float)((double)p.z - oz);
       r.w = __int_as_float(id);
       sorted_ids[beg + rank] = id;
       rec[beg + rank] = r;

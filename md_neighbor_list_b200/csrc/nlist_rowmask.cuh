@@ -95,12 +95,18 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t b
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
   const uint32_t addr = smem_u32(b);
   uint32_t ok;
+#ifdef NLB_WAIT_GUARD
+  uint32_t spins = 0;
+#endif
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(addr), "r"(parity)
         : "memory");
+#ifdef NLB_WAIT_GUARD
+    if (!ok && ++spins > (1u << 24)) __trap();  // bring-up: a lost completion must fail the launch, not hang the GPU
+#endif
   } while (!ok);
 }
 // global -> shared bulk copy by the TMA engine; bytes a positive multiple of 16, both addresses 16-byte aligned
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(RM_THREADS, NLB_RM_MINB) rowmask_kernel(RowMas
   int32_t pf_s0 = 0, pf_s1 = 0;      // raw cell_start values of position n+1 (lane r < 9: run r; lane 9: own cell)
   int32_t pf2_s0 = 0, pf2_s1 = 0;    // ... of position n+2 (in flight)
   unsigned long long mb_pending = 0;  // mask base of position n+1 (lane 0; atomic in flight)
-  uint32_t phase[2] = {0u, 0u};
+  uint32_t phases = 0u;  // bit b: parity the next wait on bars[b] expects
 
   // cell -> (cx, cy, cz), stencil ranges; lane r < nruns loads the bounds of run r = (z, y), lane 9 the own cell
   auto issue_loads = [&](int32_t cell, int32_t& s0, int32_t& s1) {
@@ -353,8 +359,8 @@ __global__ void __launch_bounds__(RM_THREADS, NLB_RM_MINB) rowmask_kernel(RowMas
               rm_fetch(a.rec, win, rowraw, &bars[b], lane, lane < 9 ? d.s0[lane] : 0, lane < 9 ? d.cs[lane] : 0,
                        lane < 9 ? d.ce[lane] : 0, sc0, sc0 + ncand, slot_a0, 0, 0);
           }
-          mbar_wait(&bars[b], phase[b]);
-          phase[b] ^= 1u;
+          mbar_wait(&bars[b], (phases >> b) & 1u);
+          phases ^= 1u << b;
           if (sc0 == 0) {
             // stage the round's rows: frame of A's centre, pre-duplicated for the packed FMAs
             for (int32_t r = threadIdx.x; r < nrows; r += RM_THREADS) {
@@ -546,9 +552,6 @@ __global__ void __launch_bounds__(RM_THREADS, NLB_RM_MINB) rowmask_kernel(RowMas
       pf_s1 = pf2_s1;
     }
     __syncthreads();  // desc[b ^ 1] complete, every warp done with buffer b
-    if (warp != 0) {
-      c_cur = 0;  // overwritten below
-    }
     // every warp follows warp 0's sequence: the next cell index travels through the descriptor
     c_cur = desc[b ^ 1].cell;
   }
@@ -673,5 +676,7 @@ __global__ void __launch_bounds__(EM3_WARPS * 32, NLB_EM3_MINB) emit3_kernel(Emi
   }
   flush(true);
 }
+
+
 
 }  // namespace nlb
