@@ -679,4 +679,6 @@ __global__ void __launch_bounds__(EM3_WARPS * 32, NLB_EM3_MINB) emit3_kernel(Emi
 
 
 
+
+
 }  // namespace nlb
