@@ -119,6 +119,14 @@ int nlb200_create(double search_length, double lx, double ly, double lz, int dty
  * run-time options.  Must be called before nlb200_initialize. */
 int nlb200_set_option(nlb200_handle h, int option, int64_t value);
 
+/* Multi-GPU (no reference counterpart): restricts the handle's cell grid along `axis` to the cells
+ * [first_cell, first_cell + n_cells) of the global grid (mesh = int(L / search_length) cells, nlb200_get_stats().mesh).
+ * Particles are still assigned to cells on the GLOBAL grid — the rows of a slab rank stay bit-identical to the rows
+ * a single-GPU build gives those particles — but the rank bins, sorts and searches only the cells of its slab plus
+ * the ghost layer instead of a grid that is mostly empty.  Every particle given to the handle must fall inside the
+ * window (else NLB200_ERR_OUT_OF_BOX).  n_cells: 1, 2 or >= 4 (or the whole axis).  Before nlb200_initialize. */
+int nlb200_set_cell_window(nlb200_handle h, int axis, int32_t first_cell, int32_t n_cells);
+
 /* Replaces Initialize(particle_number) (neighlist_gpu.hpp:268-287, neighlist_cpu.hpp:408-415): allocates for up to
  * max_particles.  max_entries is the partner-list capacity; 0 = estimate from the density max_particles/(Lx*Ly*Lz)
  * (the reference hand-edits MAX_PARTNERS per density, neighlist_gpu.hpp:70-71). */
@@ -250,6 +258,15 @@ int nlb200_pack_slab2(const void* q_dev, const int32_t* gids_dev, int64_t n, int
                       double cut_lo, double cut_hi, void* out_q_lo_dev, int32_t* out_gid_lo_dev, void* out_q_hi_dev,
                       int32_t* out_gid_hi_dev, int64_t capacity, int64_t* out_counts_dev, void* workspace_dev,
                       int64_t workspace_bytes, void* stream);
+
+/* The same selection in ONE kernel launch (what a slab rank runs before every build): positions from atomics, so the
+ * ghosts of a face arrive in no particular order — nlb200_build_subset sorts a cell's particles by global id, its
+ * rows do not depend on it.  state_dev: 32 bytes of device memory the caller zeroes ONCE (the kernel leaves them
+ * zeroed); out_counts_dev[0..1] receive the two true counts (> capacity = overflow); unused slots hold NaN records. */
+int nlb200_pack_faces(const void* q_dev, const int32_t* gids_dev, int64_t n, int dtype, int stride, int axis,
+                      double cut_lo, double cut_hi, void* out_q_lo_dev, int32_t* out_gid_lo_dev, void* out_q_hi_dev,
+                      int32_t* out_gid_hi_dev, int64_t capacity, int64_t* out_counts_dev, void* state_dev,
+                      void* stream);
 
 /* Bytes of workspace nlb200_select_slab / nlb200_pack_slab need for n particles. */
 int64_t nlb200_select_slab_workspace(int64_t n);

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libnlist_b200.so")
+# NLB200_LIB: an alternative build of the same library (tuning experiments, tools/gpu_tune.sh)
+LIB_PATH = os.environ.get("NLB200_LIB") or os.path.join(HERE, "lib", "libnlist_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_OUT_OF_BOX, ERR_ELL_ROWS, ERR_STATE, ERR_CELL_CAPACITY = range(8)
 F32, F64 = 0, 1
@@ -17,6 +18,7 @@ HALF_CSR, FULL_CSR, FULL_ELL_TRANSPOSED = 0, 1, 2
 OPT_POSITION_STRIDE, OPT_SORT_ROWS, OPT_ELL_ROWS, OPT_EXACT_ONLY, OPT_USE_GRAPH, OPT_KERNEL_VARIANT = 1, 2, 3, 4, 5, 6
 OPT_PROFILE = 7
 OPT_MAX_IN_CELL = 8
+OPT_PDL = 9
 
 
 class Stats(C.Structure):
@@ -33,6 +35,7 @@ SYMBOLS = {
     "nlb200_status_string": (C.c_char_p, [C.c_int]),
     "nlb200_create": (C.c_int, [_dbl, _dbl, _dbl, _dbl, _i32, _i32, C.POINTER(_vp)]),
     "nlb200_set_option": (C.c_int, [_vp, _i32, _i64]),
+    "nlb200_set_cell_window": (C.c_int, [_vp, _i32, C.c_int32, C.c_int32]),
     "nlb200_initialize": (C.c_int, [_vp, _i64, _i64]),
     "nlb200_reserve": (C.c_int, [_vp, _i64]),
     "nlb200_reserve_cell_capacity": (C.c_int, [_vp, _i64]),
@@ -64,6 +67,7 @@ SYMBOLS = {
     "nlb200_pack_slab": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _i32, _dbl, _dbl, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "nlb200_pack_slab2": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64,
                                     _vp]),
+    "nlb200_pack_faces": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "nlb200_select_slab_workspace": (_i64, [_i64]),
     "nlb200_shift_axis": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _dbl, _vp]),
     "nlb200_gather_records": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),

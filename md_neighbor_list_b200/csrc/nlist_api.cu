@@ -17,6 +17,10 @@
 #include "nlist_kernels.cuh"
 #include "nlist_rowmask.cuh"
 
+#ifndef NLB_RM4_RJ
+#define NLB_RM4_RJ 8  // candidates per lane of the row-mask search (packed in pairs)
+#endif
+
 using namespace nlb;
 
 struct nlb200_context {
@@ -26,7 +30,8 @@ struct nlb200_context {
   int stride = 4, sort_rows = 0, ell_rows = 200, exact_only = 0, use_graph = 1, variant = 0, profile = 0;
   GridParams<double> gp64;
   GridParams<float> gp32;
-  int32_t mesh[3] = {0, 0, 0};
+  int32_t mesh[3] = {0, 0, 0};   // cells per axis of the handle's grid (the window, if one is set)
+  int32_t gmesh[3] = {0, 0, 0};  // ... of the global grid
   int64_t n_cells = 0;
   bool initialized = false;
   int device = 0;
@@ -43,6 +48,10 @@ struct nlb200_context {
   unsigned long long* scan_state_counts = nullptr;
   DeviceStatus* status_dev = nullptr;
   unsigned long long* queue = nullptr;  // work counter of the persistent pair-mask kernel (inside zero_region)
+  unsigned int* ticket = nullptr;       // CTA ticket of bin_kernel's last-CTA scan (inside zero_region)
+  size_t status_off = 0;                // byte offset of the status block inside zero_region
+  int path = 0;                         // PATH_*: which search / emission pair the handle runs (pick_path)
+  bool state_clean = false;             // the zero region is all zero (left so by the last build's finalize_kernel)
   int sm_count = 148;
   int64_t l2_bytes = 0;
   int32_t* cell_start = nullptr;
@@ -138,6 +147,8 @@ bool make_grid(double sl, const double* L, GridParams<T>* g) {
     const int32_t m = (int32_t)(l / slt);
     if (m < 3) return false;
     g->mesh[d] = m;
+    g->gmesh[d] = m;
+    g->coff[d] = 0;
     g->ms[d] = l / (T)m;
     g->ims[d] = (T)(1.0 / (double)g->ms[d]);
     g->msf[d] = (float)g->ms[d];
@@ -323,14 +334,25 @@ cudaError_t launch_search(bool half, bool fill, bool exact, const SearchArgs<T>&
 }
 
 
-// Which search/emission pair a handle runs (NLB200_OPT_KERNEL_VARIANT):
-//   0 (default), 5: row masks      — rowmask_kernel + emit3_kernel (nlist_rowmask.cuh)
-//   1, or NLB200_OPT_EXACT_ONLY:   — search_kernel twice (count, fill): every test in the input precision if asked
-//   2, 3, 4, 7, 100..:             — round-1 pair masks (pairmask_kernel, rowcount_kernel, emit_kernel) and its ablations
-bool uses_v1(const nlb200_context* h) { return h->exact_only != 0 || h->variant == 1; }
-bool uses_rowmask(const nlb200_context* h) {
-  return !uses_v1(h) && (h->variant == 0 || h->variant == 5);
+// Which search / emission pair a handle runs.  NLB200_OPT_KERNEL_VARIANT:
+//   0 (default): PAIR MASKS (pairmask_kernel, rowcount_kernel, emit_kernel) while the per-particle mask planes stay
+//                small — their size is 108 * ceil(max_in_cell / 32) bytes per particle — and ROW MASKS
+//                (rowmask4_kernel, emit3_kernel: one bit per test, a block per cell from a cursor) once a cell may
+//                hold more than PAIRMASK_MAX_CELL particles (clustered inputs): nlb200_reserve_cell_capacity switches.
+//                On the density-1.0 default system the two pairs are within 3 % of each other (157.7 vs 161.8 us).
+//   1, or NLB200_OPT_EXACT_ONLY: search_kernel twice (count, fill): every test in the input precision if asked
+//   2, 3, 4, 7, 100..:           pair masks and their ablations
+//   5: row masks with the CTA-per-cell search (rowmask_kernel)      6, 20..39: row masks (rowmask4_kernel)
+enum { PATH_V1 = 1, PATH_PAIRMASK = 2, PATH_ROWMASK = 3 };
+constexpr int64_t PAIRMASK_MAX_CELL = 256;
+int pick_path(const nlb200_context* h, int64_t max_in_cell) {
+  if (h->exact_only != 0 || h->variant == 1) return PATH_V1;
+  if (h->variant == 5 || h->variant == 6 || (h->variant >= 20 && h->variant < 40)) return PATH_ROWMASK;
+  if (h->variant != 0) return PATH_PAIRMASK;
+  return max_in_cell > PAIRMASK_MAX_CELL ? PATH_ROWMASK : PATH_PAIRMASK;
 }
+bool uses_v1(const nlb200_context* h) { return h->path == PATH_V1; }
+bool uses_rowmask(const nlb200_context* h) { return h->path == PATH_ROWMASK; }
 
 template <typename T, int STRIDE, int HALFMODE>
 cudaError_t set_rm_attr_h() {
@@ -365,6 +387,45 @@ int launch_rowmask_h(nlb200_context* h, const RowMaskArgs<T>& a, cudaStream_t s)
   CK(h, launch_chain(rowmask_kernel<T, STRIDE, HALFMODE, 8>, dim3((unsigned)grid), dim3(RM_THREADS), smem, s, a));
   return NLB200_OK;
 }
+template <typename T, int STRIDE, int HALFMODE>
+int launch_rowmask4_h(nlb200_context* h, RowMask4Args<T>& a, cudaStream_t s) {
+  const size_t smem = sizeof(Rm4Smem<NLB_RM4_RJ>) * RM_WARPS;
+  int per_sm = 0;
+  CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rowmask4_kernel<T, STRIDE, HALFMODE, NLB_RM4_RJ>, RM_THREADS,
+                                                      smem));
+  if (per_sm < 1) return fail(h, NLB200_ERR_CUDA, "row-mask kernel does not fit an SM (%zu bytes of shared memory)", smem);
+  int64_t grid = (int64_t)per_sm * h->sm_count;
+  const int64_t units = (int64_t)a.gp.n_cells * a.upc;
+  if (grid * RM_WARPS > units) grid = (units + RM_WARPS - 1) / RM_WARPS;
+  CK(h, launch_chain(rowmask4_kernel<T, STRIDE, HALFMODE, NLB_RM4_RJ>, dim3((unsigned)grid), dim3(RM_THREADS), smem, s, a));
+  return NLB200_OK;
+}
+template <typename T, int STRIDE>
+int launch_rowmask4(nlb200_context* h, int halfmode, RowMask4Args<T>& a, cudaStream_t s) {
+  if (halfmode == 0) return launch_rowmask4_h<T, STRIDE, 0>(h, a, s);
+  if (halfmode == 1) return launch_rowmask4_h<T, STRIDE, 1>(h, a, s);
+  return launch_rowmask4_h<T, STRIDE, 2>(h, a, s);
+}
+template <typename T, int STRIDE, int HALFMODE>
+cudaError_t set_rm4_attr_h() {
+  return cudaFuncSetAttribute(rowmask4_kernel<T, STRIDE, HALFMODE, NLB_RM4_RJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              MAX_EMIT_SMEM);
+}
+template <typename T, int STRIDE>
+cudaError_t set_rm4_attr() {
+  cudaError_t e;
+  if ((e = set_rm4_attr_h<T, STRIDE, 0>()) != cudaSuccess) return e;
+  if ((e = set_rm4_attr_h<T, STRIDE, 1>()) != cudaSuccess) return e;
+  return set_rm4_attr_h<T, STRIDE, 2>();
+}
+cudaError_t set_rowmask4_attrs() {
+  cudaError_t e;
+  if ((e = set_rm4_attr<double, 4>()) != cudaSuccess) return e;
+  if ((e = set_rm4_attr<double, 3>()) != cudaSuccess) return e;
+  if ((e = set_rm4_attr<float, 4>()) != cudaSuccess) return e;
+  return set_rm4_attr<float, 3>();
+}
+
 template <typename T, int STRIDE>
 int launch_rowmask(nlb200_context* h, int halfmode, const RowMaskArgs<T>& a, cudaStream_t s) {
   if (halfmode == 0) return launch_rowmask_h<T, STRIDE, 0>(h, a, s);
@@ -401,16 +462,24 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     return cudaEventRecord(h->ev[h->n_stages++], s);
   };
   CK(h, stage(ST_ZERO));
-  CK(h, cudaMemsetAsync(h->zero_region, 0, h->zero_bytes, s));
+  // every build leaves the per-build state zeroed (finalize_kernel); only a build that follows a failed enqueue
+  // clears it itself
+  if (!h->state_clean) CK(h, cudaMemsetAsync(h->zero_region, 0, h->zero_bytes, s));
+  h->state_clean = false;
   CK(h, stage(ST_BIN));
+  const bool scan_in_bin = n > 0 && M <= BIN_SCAN_MAX_CELLS;
   if (n > 0) {
-    // first kernel of the chain: a plain launch behind the memset
-    bin_kernel<T, STRIDE><<<(n + 255) / 256, 256, 0, s>>>(q, n, (int32_t)n_owned, gp, h->cell_count, h->cell_rank,
-                                                          h->status_dev);
+    // first kernel of the chain: a plain launch
+    if (scan_in_bin)
+      bin_kernel<T, STRIDE, true><<<(n + 255) / 256, 256, 0, s>>>(q, n, (int32_t)n_owned, gp, h->cell_count, h->cell_rank,
+                                                                  h->status_dev, h->cell_start, h->ticket);
+    else
+      bin_kernel<T, STRIDE, false><<<(n + 255) / 256, 256, 0, s>>>(q, n, (int32_t)n_owned, gp, h->cell_count,
+                                                                   h->cell_rank, h->status_dev, h->cell_start, h->ticket);
     CK(h, cudaGetLastError());
   }
   CK(h, stage(ST_SCAN_CELLS));
-  {
+  if (!scan_in_bin) {
     const int tiles = (int)((M + SCAN_TILE - 1) / SCAN_TILE);
     const bool after_kernel = n > 0;  // n == 0: the scan follows the memset directly
     const bool keep = t_pdl;
@@ -427,14 +496,20 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     CK(h, stage(ST_CELLSORT));
     int64_t cs_blocks = ((int64_t)M * 32 + 127) / 128;
     if (cs_blocks > (int64_t)h->sm_count * 64) cs_blocks = (int64_t)h->sm_count * 64;  // warps stride over the cells
+    // cells per warp batch: 1 while every warp gets about one cell, up to 32 on large grids (see cellsort_kernel)
+    int32_t cs_batch = (int32_t)((int64_t)M / (cs_blocks * 4 * 2));
+    if (cs_batch < 1) cs_batch = 1;
+    if (cs_batch > 32) cs_batch = 32;
     if (uses_rowmask(h))
+      // variant 5 (the CTA-per-cell search) writes the cell records itself
       CK(h, launch_chain(cellsort_kernel<T, STRIDE, true>, dim3((unsigned)cs_blocks), dim3(128), 0, s, q, gp,
                          (const int32_t*)h->cell_start, (const int32_t*)h->perm, h->sorted_ids, h->rec, h->slot_cell,
-                         gids, h->slot_gid));
+                         gids, h->slot_gid, h->variant == 5 ? (CellRec*)nullptr : h->cellrec,
+                         (unsigned long long)h->rmask_cap, h->counts, (int32_t)n_owned, h->status_dev, cs_batch));
     else
       CK(h, launch_chain(cellsort_kernel<T, STRIDE, false>, dim3((unsigned)cs_blocks), dim3(128), 0, s, q, gp,
                          (const int32_t*)h->cell_start, (const int32_t*)h->perm, h->sorted_ids, h->rec, h->slot_cell,
-                         gids, h->slot_gid));
+                         gids, h->slot_gid, (CellRec*)nullptr, 0ull, (int32_t*)nullptr, 0, h->status_dev, 1));
   }
   const bool half = h->mode == NLB200_HALF_CSR;
   const bool use_v1 = uses_v1(h);
@@ -459,8 +534,35 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     rm.queue = h->queue;
     rm.st = h->status_dev;
     CK(h, stage(ST_ROWMASK));
-    if (n > 0) {
+    if (n > 0 && h->variant == 5) {
       const int rc = launch_rowmask<T, STRIDE>(h, !half ? 0 : (gids == nullptr ? 1 : 2), rm, s);
+      if (rc) return rc;
+    } else if (n > 0) {
+      RowMask4Args<T> r4;
+      r4.q = q;
+      r4.gp = gp;
+      r4.cell_start = h->cell_start;
+      r4.rec = h->rec;
+      r4.global_ids = gids;
+      r4.n_owned = (int32_t)n_owned;
+      r4.mask = h->rmask;
+      r4.mask_cap = (unsigned long long)h->rmask_cap;
+      r4.cellrec = h->cellrec;
+      r4.counts = h->counts;
+      // parts per cell: one warp-sized chunk of 256 candidates each for a mean window; crowded cells loop inside
+      int64_t upc = (int64_t)(27.0 * ((double)n / (double)M) / (32.0 * NLB_RM4_RJ) + 0.999);
+      if (h->variant >= 20 && h->variant < 40) upc = h->variant - 20;  // tuning override
+      if (upc < 1) upc = 1;
+      if (upc > 8) upc = 8;
+      if ((int64_t)M * upc >= (1ll << 31)) return fail(h, NLB200_ERR_INVALID, "cells x parts exceeds 2^31 units");
+      r4.upc = (int32_t)upc;
+      r4.d_mx = make_fastdiv((uint32_t)gp.mesh[0]);
+      r4.d_my = make_fastdiv((uint32_t)gp.mesh[1]);
+      r4.d_upc = make_fastdiv((uint32_t)upc);
+      r4.band = h->band_v3;
+      r4.queue = reinterpret_cast<unsigned int*>(h->queue);
+      r4.st = h->status_dev;
+      const int rc = launch_rowmask4<T, STRIDE>(h, !half ? 0 : (gids == nullptr ? 1 : 2), r4, s);
       if (rc) return rc;
     }
     CK(h, stage(ST_SCAN_COUNTS));
@@ -635,7 +737,16 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
                        h->ell_prev, (long long)h->cap_entries, h->status_dev));
   }
   CK(h, stage(ST_STATUS));
-  CK(h, cudaMemcpyAsync(h->status_host, h->status_dev, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, s));
+  {
+    const size_t vecs = h->zero_bytes / 16;
+    unsigned fgrid = (unsigned)((vecs + 1023) / 1024);
+    if (fgrid < 1) fgrid = 1;
+    if (fgrid > (unsigned)h->sm_count * 4) fgrid = (unsigned)h->sm_count * 4;
+    CK(h, launch_chain(finalize_kernel, dim3(fgrid), dim3(256), 0, s, h->status_dev, h->status_host,
+                       reinterpret_cast<uint4*>(h->zero_region), vecs, h->status_off / 16,
+                       (sizeof(DeviceStatus) + 15) / 16));
+  }
+  h->state_clean = true;
   if (h->profile) CK(h, cudaEventRecord(h->ev[h->n_stages], s));
   return NLB200_OK;
 }
@@ -696,6 +807,50 @@ int alloc_rmask(nlb200_context* h, int64_t words) {
   if (h->rmask) cudaFree(h->rmask);
   h->rmask = fresh;
   h->rmask_cap = words;
+  return NLB200_OK;
+}
+
+// Buffers of the handle's search path for cells of up to `mic` particles.
+int alloc_search_buffers(nlb200_context* h, int64_t mic) {
+  const int64_t n = h->max_n > 0 ? h->max_n : 1;
+  const int64_t M = h->n_cells;
+  if (uses_rowmask(h)) {
+    if (!h->cellrec) CK(h, cudaMalloc(&h->cellrec, sizeof(CellRec) * (size_t)M));
+    // one bit per test: rows x ceil(27 cells x mic / 32) words bounds a uniform density; clustered inputs report
+    // NLB200_ERR_CELL_CAPACITY with the exact need and nlb200_reserve_cell_capacity grows the buffer to it
+    int64_t per_row = (27 * std::min<int64_t>(mic, 96) + 31) / 32 + 1;
+    const int64_t words = std::max<int64_t>(n * per_row + 4096, h->rmask_need + h->rmask_need / 16 + 4096);
+    if (words > h->rmask_cap) {
+      const int rc = alloc_rmask(h, words);
+      if (rc) return rc;
+    }
+    // window round of the CTA-per-cell search (variant 5): ~1.2 x the mean window, in chunks of 256 candidates
+    const double avg = (double)n / (double)M;
+    int64_t wc = (int64_t)(27.0 * (avg > 1.0 ? avg : 1.0) * 1.2);
+    wc = (wc + 255) / 256 * 256;
+    if (wc < 512) wc = 512;
+    if (wc > 6144) wc = 6144;
+    h->win_cap = (int32_t)wc;
+    // band of the FP32 pre-filter for absolute FP32 records: the evaluation error in the cell frame (384 u ms^2,
+    // DESIGN.md §6) plus what the rounding of both particles' coordinates to FP32 can move (SL^2 - r^2)/2 inside
+    // r < 2 SL: 2 SL * 2 sqrt(3) * ulp(max |coordinate|)/2 < 8 SL * eps_abs
+    double lmax = 0, msmax = 0;
+    for (int d = 0; d < 3; d++) {
+      lmax = std::max(lmax, h->L[d]);
+      msmax = std::max(msmax, h->L[d] / (double)h->gmesh[d]);
+    }
+    int ex = 0;
+    std::frexp(lmax + 2.0 * msmax, &ex);  // value < 2^ex: ulp = 2^(ex - 24)
+    const double eps_abs = h->dtype == NLB200_F64 ? std::ldexp(1.0, ex - 25) : 0.0;
+    h->band_v3 = (float)(384.0 * std::ldexp(1.0, -24) * msmax * msmax + 8.0 * h->sl * eps_abs);
+    if (h->mask) {  // the handle came from the pair-mask path
+      cudaFree(h->mask);
+      h->mask = nullptr;
+      h->mask_wi = 0;
+    }
+    return NLB200_OK;
+  }
+  if (!uses_v1(h)) return alloc_mask(h, mic);
   return NLB200_OK;
 }
 
@@ -761,7 +916,7 @@ int nlb200_create(double search_length, double lx, double ly, double lz, int dty
     return NLB200_ERR_INVALID;
   }
   const int32_t* m = (dtype == NLB200_F64) ? h->gp64.mesh : h->gp32.mesh;
-  for (int d = 0; d < 3; d++) h->mesh[d] = m[d];
+  for (int d = 0; d < 3; d++) h->mesh[d] = h->gmesh[d] = m[d];
   h->n_cells = (int64_t)m[0] * m[1] * m[2];
   *out = h;
   return NLB200_OK;
@@ -793,6 +948,28 @@ int nlb200_set_option(nlb200_handle h, int option, int64_t value) {
   return fail(h, NLB200_ERR_INVALID, "unknown option %d", option);
 }
 
+int nlb200_set_cell_window(nlb200_handle h, int axis, int32_t first_cell, int32_t n_cells) {
+  if (!h) return NLB200_ERR_INVALID;
+  if (h->initialized) return fail(h, NLB200_ERR_STATE, "the cell window must be set before nlb200_initialize");
+  if (axis < 0 || axis > 2) return fail(h, NLB200_ERR_INVALID, "axis out of range");
+  const int32_t gm = h->gmesh[axis];
+  if (first_cell < 0 || n_cells < 1 || first_cell + (int64_t)n_cells > gm)
+    return fail(h, NLB200_ERR_INVALID, "cell window [%d, %d) outside the grid of %d cells", first_cell,
+                first_cell + n_cells, gm);
+  // a 3-cell axis is special-cased as fully connected (the reference's wrapped stencil, axis_range): a WINDOW of
+  // exactly 3 cells of a longer axis must not be
+  if (n_cells == 3 && gm != 3) return fail(h, NLB200_ERR_INVALID, "a cell window needs 1, 2 or at least 4 cells");
+  auto apply = [&](auto& gp) {
+    gp.mesh[axis] = n_cells;
+    gp.coff[axis] = first_cell;
+    gp.n_cells = gp.mesh[0] * gp.mesh[1] * gp.mesh[2];
+  };
+  if (h->dtype == NLB200_F64) apply(h->gp64); else apply(h->gp32);
+  h->mesh[axis] = n_cells;
+  h->n_cells = (int64_t)h->mesh[0] * h->mesh[1] * h->mesh[2];
+  return NLB200_OK;
+}
+
 int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entries) {
   if (!h) return NLB200_ERR_INVALID;
   if (max_particles < 0 || max_particles > 2147483647ll - 64)
@@ -803,6 +980,7 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
   CK(h, cudaGetDevice(&h->device));
   CK(h, set_search_attrs());
   CK(h, set_rowmask_attrs());
+  CK(h, set_rowmask4_attrs());
   free_buffers(h);
   const int64_t n = max_particles > 0 ? max_particles : 1;
   const int64_t M = h->n_cells;
@@ -821,13 +999,19 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
   off = align_up(off + sizeof(DeviceStatus), 256);
   const size_t o_q = off;
   off = align_up(off + sizeof(unsigned long long), 256);
+  const size_t o_t = off;
+  off = align_up(off + sizeof(unsigned int), 256);
   h->zero_bytes = off;
+  h->status_off = o_st;
   CK(h, cudaMalloc(&h->zero_region, off));
+  CK(h, cudaMemset(h->zero_region, 0, off));
+  h->state_clean = true;
   h->cell_count = reinterpret_cast<int32_t*>(h->zero_region + o_count);
   h->scan_state_cells = reinterpret_cast<unsigned long long*>(h->zero_region + o_sc);
   h->scan_state_counts = reinterpret_cast<unsigned long long*>(h->zero_region + o_sn);
   h->status_dev = reinterpret_cast<DeviceStatus*>(h->zero_region + o_st);
   h->queue = reinterpret_cast<unsigned long long*>(h->zero_region + o_q);
+  h->ticket = reinterpret_cast<unsigned int*>(h->zero_region + o_t);
   CK(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
   {
     int l2 = 0;
@@ -851,36 +1035,9 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
   if (rc) return rc;
   {
     const int64_t mic = h->max_in_cell_opt > 0 ? h->max_in_cell_opt : estimate_max_in_cell(h, n);
-    if (uses_rowmask(h)) {
-      CK(h, cudaMalloc(&h->cellrec, sizeof(CellRec) * (size_t)M));
-      // one bit per test: rows x ceil(27 cells x mic / 32) words is a bound for a uniform density; clustered inputs
-      // report NLB200_ERR_CELL_CAPACITY with the exact need and nlb200_reserve_cell_capacity grows the buffer
-      const int64_t per_row = (27 * mic + 31) / 32 + 1;
-      rc = alloc_rmask(h, n * per_row + 4096);
-      if (rc) return rc;
-      // window round: ~1.2 x the mean window, in chunks of 256 candidates (8 per lane), 512..6144
-      const double avg = (double)n / (double)M;
-      int64_t wc = (int64_t)(27.0 * (avg > 1.0 ? avg : 1.0) * 1.2);
-      wc = (wc + 255) / 256 * 256;
-      if (wc < 512) wc = 512;
-      if (wc > 6144) wc = 6144;
-      h->win_cap = (int32_t)wc;
-      // band of the FP32 pre-filter for absolute FP32 records: the evaluation error in the cell frame (384 u ms^2,
-      // DESIGN.md §6) plus what the rounding of both particles' coordinates to FP32 can move (SL^2 - r^2)/2 inside
-      // r < 2 SL: 2 SL * 2 sqrt(3) * ulp(max |coordinate|)/2 < 8 SL * eps_abs
-      double lmax = 0, msmax = 0;
-      for (int d = 0; d < 3; d++) {
-        lmax = std::max(lmax, h->L[d]);
-        msmax = std::max(msmax, h->L[d] / (double)h->mesh[d]);
-      }
-      int ex = 0;
-      std::frexp(lmax + 2.0 * msmax, &ex);  // value < 2^ex: ulp = 2^(ex - 24)
-      const double eps_abs = h->dtype == NLB200_F64 ? std::ldexp(1.0, ex - 25) : 0.0;
-      h->band_v3 = (float)(384.0 * std::ldexp(1.0, -24) * msmax * msmax + 8.0 * h->sl * eps_abs);
-    } else if (!uses_v1(h)) {
-      rc = alloc_mask(h, mic);
-      if (rc) return rc;
-    }
+    h->path = pick_path(h, mic);
+    rc = alloc_search_buffers(h, mic);
+    if (rc) return rc;
   }
   if (h->mode == NLB200_FULL_ELL_TRANSPOSED) {
     // neighlist_gpu.hpp:102,271-274: MAX_PARTNERS * N ints, filled with -1 once
@@ -911,6 +1068,7 @@ int nlb200_reserve(nlb200_handle h, int64_t max_entries) {
 
 int nlb200_reserve_cell_capacity(nlb200_handle h, int64_t max_in_cell) {
   if (!h || !h->initialized) return h ? fail(h, NLB200_ERR_STATE, "reserve before initialize") : NLB200_ERR_INVALID;
+  if (uses_v1(h)) return NLB200_OK;
   if (uses_rowmask(h)) {
     // the row-mask buffer holds one bit per test: grow it to what the failed build asked for (+ 1/16)
     const int64_t need = h->rmask_need + h->rmask_need / 16 + 4096;
@@ -918,8 +1076,15 @@ int nlb200_reserve_cell_capacity(nlb200_handle h, int64_t max_in_cell) {
     CK(h, settle_before_realloc(h));
     return alloc_rmask(h, need);
   }
-  if (uses_v1(h) || max_in_cell <= (int64_t)h->mask_wi * 32) return NLB200_OK;
+  if (max_in_cell <= (int64_t)h->mask_wi * 32) return NLB200_OK;
   CK(h, settle_before_realloc(h));
+  if (pick_path(h, max_in_cell) == PATH_ROWMASK) {
+    // crowded cells: the per-particle planes of the pair masks would grow with the most crowded cell; the row masks
+    // grow with the number of tests.  The first build on the new path reports how many words it needs.
+    h->path = PATH_ROWMASK;
+    h->rmask_need = 0;
+    return alloc_search_buffers(h, max_in_cell);
+  }
   return alloc_mask(h, max_in_cell);
 }
 
@@ -982,7 +1147,10 @@ int nlb200_build_subset(nlb200_handle h, const void* q_dev, int64_t n_total, int
           }
         }
         if (graph) cudaGraphDestroy(graph);
-        if (rc != NLB200_OK) return rc;
+        if (rc != NLB200_OK) {
+          drop_graph(h);
+          return rc;
+        }
       }
       (void)cudaGetLastError();
     }
@@ -994,7 +1162,10 @@ int nlb200_build_subset(nlb200_handle h, const void* q_dev, int64_t n_total, int
   } else {
     rc = enqueue_dispatch(h, q_dev, n_total, n_owned, global_ids_dev, s);
   }
-  if (rc != NLB200_OK) return rc;
+  if (rc != NLB200_OK) {
+    drop_graph(h);  // a failed enqueue leaves the per-build state dirty: the next build clears it itself
+    return rc;
+  }
   h->last_stream = s;
   h->build_pending = true;
   h->have_result = false;
@@ -1032,7 +1203,7 @@ int nlb200_synchronize(nlb200_handle h) {
   h->stats.band_tests = (int64_t)st.band_tests;
   h->stats.required_entries = (int64_t)st.total_entries;
   h->stats.capacity_entries = h->cap_entries;
-  for (int d = 0; d < 3; d++) h->stats.mesh[d] = h->mesh[d];
+  for (int d = 0; d < 3; d++) h->stats.mesh[d] = h->gmesh[d];
   h->stats.max_partners = st.max_partners;
   h->stats.max_in_cell = st.max_in_cell;
   h->rmask_need = (int64_t)st.mask_words;
@@ -1068,7 +1239,9 @@ int nlb200_build_host(nlb200_handle h, const void* q_host, int64_t n, int32_t* n
   int rc = nlb200_build(h, h->q_stage, n, s);
   if (rc) return rc;
   rc = nlb200_synchronize(h);
-  if (rc == NLB200_ERR_CELL_CAPACITY) {
+  for (int attempt = 0; attempt < 3 && rc == NLB200_ERR_CELL_CAPACITY; attempt++) {
+    // crowded cells: grow the masks (the first growth may move the handle to the row-mask path, whose first build
+    // then reports how many words it needs)
     rc = nlb200_reserve_cell_capacity(h, h->stats.max_in_cell);
     if (rc) return rc;
     rc = nlb200_build(h, h->q_stage, n, s);
@@ -1135,7 +1308,7 @@ int nlb200_get_stats(nlb200_handle h, nlb200_stats* out) {
   if (!h || !out) return NLB200_ERR_INVALID;
   if (!h->have_result) {
     nlb200_stats s{};
-    for (int d = 0; d < 3; d++) s.mesh[d] = h->mesh[d];
+    for (int d = 0; d < 3; d++) s.mesh[d] = h->gmesh[d];
     s.capacity_entries = h->cap_entries;
     *out = s;
     return NLB200_OK;
@@ -1374,6 +1547,27 @@ int nlb200_pack_slab2(const void* q_dev, const int32_t* gids_dev, int64_t n, int
     return NLB200_ERR_CUDA;
   }
   return NLB200_OK;
+}
+
+int nlb200_pack_faces(const void* q_dev, const int32_t* gids_dev, int64_t n, int dtype, int stride, int axis,
+                      double cut_lo, double cut_hi, void* out_q_lo_dev, int32_t* out_gid_lo_dev, void* out_q_hi_dev,
+                      int32_t* out_gid_hi_dev, int64_t capacity, int64_t* out_counts_dev, void* state_dev,
+                      void* stream) {
+  if (n < 0 || capacity < 0 || axis < 0 || axis > 2 || (stride != 3 && stride != 4) || !state_dev || !out_counts_dev)
+    return NLB200_ERR_INVALID;
+  (void)cudaGetLastError();  // a non-sticky error left behind by another library must not be reported as ours
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned g = (unsigned)((n + 255) / 256 > 0 ? (n + 255) / 256 : 1);
+  unsigned long long* st = reinterpret_cast<unsigned long long*>(state_dev);
+  if (dtype == NLB200_F64)
+    pack_faces_kernel<double><<<g, 256, 0, s>>>((const double*)q_dev, gids_dev, n, stride, axis, cut_lo, cut_hi,
+                                               (double*)out_q_lo_dev, out_gid_lo_dev, (double*)out_q_hi_dev,
+                                               out_gid_hi_dev, capacity, st, out_counts_dev);
+  else
+    pack_faces_kernel<float><<<g, 256, 0, s>>>((const float*)q_dev, gids_dev, n, stride, axis, cut_lo, cut_hi,
+                                              (float*)out_q_lo_dev, out_gid_lo_dev, (float*)out_q_hi_dev,
+                                              out_gid_hi_dev, capacity, st, out_counts_dev);
+  return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
 }
 
 int64_t nlb200_select_slab_workspace(int64_t n) {

@@ -54,10 +54,27 @@ struct DeviceStatus {
   unsigned long long mask_words;  // row-mask words requested by the cells (cursor of the per-cell blocks)
 };
 
+constexpr uint32_t FLAG_MASK_WORDS = 32u;  // the row-mask buffer is too small (status.mask_words tells the need)
+
+// What the row-mask search and the emission need to know about a cell (nlist_rowmask.cuh).  The candidates of a cell
+// are the <= 9 contiguous x-runs of its stencil in the cell-sorted arrays, concatenated: its "candidate list".
+struct alignas(8) CellRec {
+  int2 run[9];  // .x: end (exclusive) of run r in the cell's candidate list; .y: first slot of run r minus its start
+                //     in the list, so that slot = candidate index + .y.  Absent runs: .x = nj.
+  int32_t nj;         // candidates of the cell (length of the list)
+  int32_t self_base;  // candidate index of the cell's own first particle
+  unsigned long long mask_base;  // first word of the cell's block: word (k, i) at mask_base + k * n_A + i
+};
+
 template <typename T>
 struct GridParams {
-  int32_t mesh[3];
+  int32_t mesh[3];   // cells per axis of the handle's grid
   int32_t n_cells;
+  // Cell window (nlb200_set_cell_window, multi-GPU): the handle's grid is the cells [coff, coff + mesh) of the global
+  // grid of gmesh cells per axis.  A particle's cell is computed on the GLOBAL grid — same assignment as a single-GPU
+  // build — and shifted by coff.  Without a window gmesh = mesh, coff = 0.
+  int32_t gmesh[3];
+  int32_t coff[3];
   T ims[3];  // 1/ms, rounded as the reference does (neighlist_gpu.hpp:250-252)
   T ms[3];   // cell edge (neighlist_gpu.hpp:246-248)
   T sl2;     // SL*SL rounded once in T (neighlist_gpu.hpp:254)
@@ -158,35 +175,102 @@ __device__ __forceinline__ bool exact_within(const Vec3<float>& a, const Vec3<fl
 // Here every index is clamped into [0, mesh-1], which additionally keeps particles slightly outside the box next to
 // their true neighbours; a particle more than one cell outside (or NaN) raises FLAG_OUT_OF_BOX because the FP32
 // pre-filter's error bound assumes |x - cell corner| <= 2 cells.
-template <typename T, int STRIDE>
+// SCAN_HERE: the LAST CTA to finish (ticket counter) also scans the histogram into cell_start and records the most
+// crowded cell — one kernel boundary less for grids of up to BIN_SCAN_MAX_CELLS cells (the separate look-back scan
+// serves larger grids: one CTA needs ~1 us per thousand cells).  For the default system (3375 cells) one CTA scans in ~2 us what cost a launch of its own.
+constexpr int BIN_SCAN_MAX_CELLS = 1 << 13;
+template <typename T, int STRIDE, bool SCAN_HERE>
 __global__ void __launch_bounds__(256) bin_kernel(const T* __restrict__ q, int32_t n, int32_t n_owned,
                                                   GridParams<T> gp, int32_t* __restrict__ cell_count,
-                                                  int2* __restrict__ cell_rank, DeviceStatus* __restrict__ st) {
+                                                  int2* __restrict__ cell_rank, DeviceStatus* __restrict__ st,
+                                                  int32_t* __restrict__ cell_start, unsigned int* __restrict__ ticket) {
   pdl_enter();
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const Vec3<T> p = load_pos<T, STRIDE>(q, i);
-  if (i >= n_owned && p.x != p.x) {
-    // an ABSENT ghost: the fixed-capacity halo buffers of the multi-GPU build are padded with NaN records
-    // (parallel.py); they take part in nothing — no cell, no slot, no row
-    cell_rank[i] = make_int2(-1, 0);
-    return;
+  if (i < n) {
+    const Vec3<T> p = load_pos<T, STRIDE>(q, i);
+    if (i >= n_owned && p.x != p.x) {
+      // an ABSENT ghost: the fixed-capacity halo buffers of the multi-GPU build are padded with NaN records
+      // (parallel.py); they take part in nothing — no cell, no slot, no row
+      cell_rank[i] = make_int2(-1, 0);
+    } else {
+      int32_t cx = static_cast<int32_t>(p.x * gp.ims[0]);
+      int32_t cy = static_cast<int32_t>(p.y * gp.ims[1]);
+      int32_t cz = static_cast<int32_t>(p.z * gp.ims[2]);
+      cx = min(max(cx, 0), gp.gmesh[0] - 1);
+      cy = min(max(cy, 0), gp.gmesh[1] - 1);
+      cz = min(max(cz, 0), gp.gmesh[2] - 1);
+      const double rx = (double)p.x - (double)cx * (double)gp.ms[0];
+      const double ry = (double)p.y - (double)cy * (double)gp.ms[1];
+      const double rz = (double)p.z - (double)cz * (double)gp.ms[2];
+      bool ok = (rx >= -(double)gp.ms[0]) && (rx <= 2.0 * (double)gp.ms[0]) && (ry >= -(double)gp.ms[1]) &&
+                (ry <= 2.0 * (double)gp.ms[1]) && (rz >= -(double)gp.ms[2]) && (rz <= 2.0 * (double)gp.ms[2]);
+      // into the handle's window of the global grid; a particle outside it was given to the wrong handle
+      cx -= gp.coff[0];
+      cy -= gp.coff[1];
+      cz -= gp.coff[2];
+      ok = ok && cx >= 0 && cx < gp.mesh[0] && cy >= 0 && cy < gp.mesh[1] && cz >= 0 && cz < gp.mesh[2];
+      cx = min(max(cx, 0), gp.mesh[0] - 1);
+      cy = min(max(cy, 0), gp.mesh[1] - 1);
+      cz = min(max(cz, 0), gp.mesh[2] - 1);
+      if (!ok) atomicOr(&st->flags, FLAG_OUT_OF_BOX);
+      const int32_t cell = cx + (cy + cz * gp.mesh[1]) * gp.mesh[0];
+      const int32_t rank = atomicAdd(&cell_count[cell], 1);
+      cell_rank[i] = make_int2(cell, rank);
+    }
   }
-  int32_t cx = static_cast<int32_t>(p.x * gp.ims[0]);
-  int32_t cy = static_cast<int32_t>(p.y * gp.ims[1]);
-  int32_t cz = static_cast<int32_t>(p.z * gp.ims[2]);
-  cx = min(max(cx, 0), gp.mesh[0] - 1);
-  cy = min(max(cy, 0), gp.mesh[1] - 1);
-  cz = min(max(cz, 0), gp.mesh[2] - 1);
-  const double rx = (double)p.x - (double)cx * (double)gp.ms[0];
-  const double ry = (double)p.y - (double)cy * (double)gp.ms[1];
-  const double rz = (double)p.z - (double)cz * (double)gp.ms[2];
-  const bool ok = (rx >= -(double)gp.ms[0]) && (rx <= 2.0 * (double)gp.ms[0]) && (ry >= -(double)gp.ms[1]) &&
-                  (ry <= 2.0 * (double)gp.ms[1]) && (rz >= -(double)gp.ms[2]) && (rz <= 2.0 * (double)gp.ms[2]);
-  if (!ok) atomicOr(&st->flags, FLAG_OUT_OF_BOX);
-  const int32_t cell = cx + (cy + cz * gp.mesh[1]) * gp.mesh[0];
-  const int32_t rank = atomicAdd(&cell_count[cell], 1);
-  cell_rank[i] = make_int2(cell, rank);
+  if (!SCAN_HERE) return;
+  // ---- the last CTA scans the histogram ----
+  __shared__ bool is_last;
+  __shared__ int32_t wsum[8], wmax[8];
+  __threadfence();  // this CTA's histogram updates are visible before its ticket
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int32_t M = gp.n_cells;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int32_t carry = 0, cmax = 0;
+  for (int32_t b0 = 0; b0 < M; b0 += 256 * 4) {
+    // 4 consecutive cells per thread
+    const int32_t c0 = b0 + threadIdx.x * 4;
+    int32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = (c0 + k < M) ? __ldcg(cell_count + c0 + k) : 0;
+    const int32_t tsum = v[0] + v[1] + v[2] + v[3];
+    int32_t incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    int32_t tm = max(max(v[0], v[1]), max(v[2], v[3]));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) tm = max(tm, __shfl_xor_sync(0xffffffffu, tm, d));
+    __syncthreads();  // the previous round's wsum readers are done
+    if (lane == 31) wsum[w] = incl;
+    if (lane == 0) wmax[w] = tm;
+    __syncthreads();
+    int32_t wpre = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int32_t s2 = wsum[k];
+      if (k < w) wpre += s2;
+      tot += s2;
+      cmax = max(cmax, wmax[k]);
+    }
+    int32_t run = carry + wpre + incl - tsum;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (c0 + k < M) cell_start[c0 + k] = run;
+      run += v[k];
+    }
+    carry += tot;
+  }
+  if (threadIdx.x == 0) {
+    cell_start[M] = carry;
+    if (cmax > 0) atomicMax(&st->max_in_cell, cmax);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -347,9 +431,15 @@ __global__ void __launch_bounds__(256) scatter_kernel(const int2* __restrict__ c
 //    sorted_ids[slot] = id, slot_cell[slot] = cell
 //    One warp per cell; rank sort with warp shuffles (O(n^2/32) per cell, n ~ 35).
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void axis_range(int c, int m, int& lo, int& hi);
+
 // ABS: records hold the ABSOLUTE coordinates rounded to FP32 (the row-mask search shifts them into a cell frame with
 // three subtractions; its band E accounts for the rounding, nlist_api.cu), else coordinates relative to the
 // particle's own cell corner (round-1 search kernels).
+// cellrec != nullptr (row-mask path): the warp also writes the cell's CellRec — run table of its candidate list, its
+// length, the cell's own position in it — takes the cell's block of the row-mask buffer from a cursor (one atomicAdd
+// per cell: the buffer holds one bit per test whatever the density profile) and zeroes the row lengths of its owned
+// particles, which the search accumulates with atomics.
 template <typename T, int STRIDE, bool ABS>
 __global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, GridParams<T> gp,
                                                        const int32_t* __restrict__ cell_start,
@@ -357,29 +447,117 @@ __global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, 
                                                        int32_t* __restrict__ sorted_ids, float4* __restrict__ rec,
                                                        int32_t* __restrict__ slot_cell,
                                                        const int32_t* __restrict__ global_ids,
-                                                       int32_t* __restrict__ slot_pid) {
+                                                       int32_t* __restrict__ slot_pid, CellRec* __restrict__ cellrec,
+                                                       unsigned long long mask_cap, int32_t* __restrict__ counts,
+                                                       int32_t n_owned, DeviceStatus* __restrict__ st, int32_t batch) {
   pdl_enter();
-  // warps stride over the cells (a slab rank bins on the global grid: most of its cells are empty)
+  // warps stride over batches of `batch` consecutive cells (a slab rank bins on the global grid: most of its cells
+  // are empty).  batch > 1 on large grids: the blocks of a batch's cells are taken from the row-mask cursor with ONE
+  // atomicAdd (lane = cell computes its need first) — one atomic per cell on a single address costs ~2 ns each,
+  // 0.9 ms at 456 k cells.
   const int lane = lane_id();
   const int32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (int32_t cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; cell < gp.n_cells; cell += warps) {
+  for (int32_t c0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * batch; c0 < gp.n_cells; c0 += warps * batch) {
+  unsigned long long batch_base = 0;
+  if (cellrec != nullptr && batch > 1) {
+    // lane = cell c0 + lane: candidates of its stencil (sum over the <= 9 runs) -> words it needs
+    unsigned long long need = 0;
+    const int32_t cl = c0 + lane;
+    if (lane < batch && cl < gp.n_cells) {
+      const int32_t na = __ldg(cell_start + cl + 1) - __ldg(cell_start + cl);
+      if (na > 0) {
+        const int32_t mx = gp.mesh[0], my = gp.mesh[1], mz = gp.mesh[2];
+        const int32_t lx = cl % mx, ly = (cl / mx) % my, lzc = cl / (mx * my);
+        int xlo, xhi, ylo, yhi, zlo, zhi;
+        axis_range(lx, mx, xlo, xhi);
+        axis_range(ly, my, ylo, yhi);
+        axis_range(lzc, mz, zlo, zhi);
+        int32_t nj = 0;
+        for (int z = zlo; z <= zhi; z++)
+          for (int y = ylo; y <= yhi; y++) {
+            const int32_t* cs = cell_start + (y + z * my) * mx;
+            nj += __ldg(cs + xhi + 1) - __ldg(cs + xlo);
+          }
+        need = (unsigned long long)na * (unsigned long long)((nj + 31) >> 5);
+      }
+    }
+    unsigned long long incl = need;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, dd);
+      if (lane >= dd) incl += v;
+    }
+    const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 0 && total > 0) {
+      base = atomicAdd(&st->mask_words, total);
+      if (base + total > mask_cap) atomicOr(&st->flags, FLAG_MASK_WORDS);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    batch_base = base + incl - need;  // lane's cell
+  }
+  for (int32_t cb = 0; cb < batch; cb++) {
+  const int32_t cell = c0 + cb;
+  if (cell >= gp.n_cells) break;
+  const unsigned long long my_base = __shfl_sync(0xffffffffu, batch_base, cb);
   const int32_t beg = __ldg(cell_start + cell);
   const int32_t cnt = __ldg(cell_start + cell + 1) - beg;
   if (cnt == 0) continue;
   const int32_t cx = cell % gp.mesh[0];
   const int32_t cy = (cell / gp.mesh[0]) % gp.mesh[1];
   const int32_t cz = cell / (gp.mesh[0] * gp.mesh[1]);
-  const double ox = (double)cx * (double)gp.ms[0], oy = (double)cy * (double)gp.ms[1],
-               oz = (double)cz * (double)gp.ms[2];
+  unsigned long long mbase = 0;
+  int32_t cr_ce = 0, cr_delta = 0, cr_nj = 0, cr_self = 0;
+  if (cellrec != nullptr) {
+    // run r = (z, y) of the stencil: the cells [xlo, xhi] of that row are contiguous in the cell-sorted arrays
+    const int32_t mx = gp.mesh[0], my = gp.mesh[1], mz = gp.mesh[2];
+    int xlo, xhi, ylo, yhi, zlo, zhi;
+    axis_range(cx, mx, xlo, xhi);
+    axis_range(cy, my, ylo, yhi);
+    axis_range(cz, mz, zlo, zhi);
+    const int32_t ny = yhi - ylo + 1, nruns = ny * (zhi - zlo + 1);
+    int32_t s0 = 0, len = 0;
+    if (lane < nruns) {
+      const int lz = lane / ny;
+      const int z = zlo + lz, y = ylo + lane - lz * ny;
+      const int32_t* cs = cell_start + (y + z * my) * mx;
+      s0 = __ldg(cs + xlo);
+      len = __ldg(cs + xhi + 1) - s0;
+    }
+    int32_t incl = len;
+#pragma unroll
+    for (int dd = 1; dd < 16; dd <<= 1) {
+      const int32_t v = __shfl_up_sync(0xffffffffu, incl, dd);
+      if (lane >= dd) incl += v;
+    }
+    cr_nj = __shfl_sync(0xffffffffu, incl, 8);
+    cr_ce = incl;
+    cr_delta = s0 - (incl - len);
+    const int r_own = (cz - zlo) * ny + (cy - ylo);
+    cr_self = __shfl_sync(0xffffffffu, incl - len, r_own) + (beg - __shfl_sync(0xffffffffu, s0, r_own));
+    if (batch > 1) {
+      mbase = my_base;
+    } else if (lane == 0) {
+      const unsigned long long need = (unsigned long long)cnt * (unsigned long long)((cr_nj + 31) >> 5);
+      mbase = atomicAdd(&st->mask_words, need);  // consumed after the id sort below
+      if (mbase + need > mask_cap) atomicOr(&st->flags, FLAG_MASK_WORDS);
+    }
+  }
+  const double ox = (double)(cx + gp.coff[0]) * (double)gp.ms[0], oy = (double)(cy + gp.coff[1]) * (double)gp.ms[1],
+               oz = (double)(cz + gp.coff[2]) * (double)gp.ms[2];
   for (int32_t eb = 0; eb < cnt; eb += 32) {
     const int32_t e = eb + lane;
     const bool valid = e < cnt;
     const int32_t id = valid ? __ldg(perm + beg + e) : 0x7fffffff;
+    // sort key: the id the rows report — with a local -> global map the GLOBAL id, so that a cell's particles come
+    // out in the order a single-GPU build of the whole system gives them, whatever order the ghosts arrived in
+    const int32_t key = (valid && global_ids != nullptr) ? __ldg(global_ids + id) : id;
     int32_t rank = 0;
     for (int32_t cb = 0; cb < cnt; cb += 32) {
-      const int32_t other = (cb + lane < cnt) ? __ldg(perm + beg + cb + lane) : 0x7fffffff;
+      int32_t other = (cb + lane < cnt) ? __ldg(perm + beg + cb + lane) : 0x7fffffff;
+      if (global_ids != nullptr && cb + lane < cnt) other = __ldg(global_ids + other);
       const int lim = min(32, cnt - cb);
-      for (int t = 0; t < lim; t++) rank += (__shfl_sync(0xffffffffu, other, t) < id) ? 1 : 0;
+      for (int t = 0; t < lim; t++) rank += (__shfl_sync(0xffffffffu, other, t) < key) ? 1 : 0;
     }
     if (valid) {
       const Vec3<T> p = load_pos<T, STRIDE>(q, id);
@@ -393,8 +571,19 @@ __global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, 
       slot_cell[beg + rank] = cell;
       // the id a row reports for this particle: with a local -> global map (multi-GPU) the emission gathers the
       // global id straight from the slot instead of slot -> local id -> global id
-      if (global_ids != nullptr) slot_pid[beg + rank] = __ldg(global_ids + id);
+      if (global_ids != nullptr) slot_pid[beg + rank] = key;
+      if (cellrec != nullptr && id < n_owned) counts[id] = 0;
     }
+  }
+  if (cellrec != nullptr) {
+    CellRec& cr = cellrec[cell];
+    if (lane < 9) cr.run[lane] = make_int2(cr_ce, cr_delta);
+    if (lane == 0) {
+      cr.nj = cr_nj;
+      cr.self_base = cr_self;
+      cr.mask_base = mbase;
+    }
+  }
   }
   }
 }
@@ -1418,6 +1607,26 @@ __global__ void __launch_bounds__(256) ell_kernel(const int64_t* __restrict__ of
   prev_count[i] = cnt;
 }
 
+// Last node of every build: the status block goes to pinned host memory (the host reads it after synchronising the
+// stream; a zero-copy store instead of a copy-engine node) and every piece of per-build state — histogram, look-back
+// words of both scans, queue, ticket, the status block itself — is cleared for the NEXT build, so that a build starts
+// without a memset node.
+__global__ void __launch_bounds__(256) finalize_kernel(DeviceStatus* __restrict__ st, DeviceStatus* __restrict__ host,
+                                                       uint4* __restrict__ zero_region, size_t zero_vecs,
+                                                       size_t status_vec0, size_t status_vecs) {
+  pdl_enter();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *host = *st;
+  // the status block is cleared by the thread that copied it (block 0 clears all of it after the copy)
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < zero_vecs; i += (size_t)gridDim.x * blockDim.x) {
+    if (i >= status_vec0 && i < status_vec0 + status_vecs) continue;
+    zero_region[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (blockIdx.x == 0) {
+    __syncthreads();
+    for (size_t i = threadIdx.x; i < status_vecs; i += blockDim.x) zero_region[status_vec0 + i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 __global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = v;
@@ -1497,6 +1706,66 @@ __global__ void __launch_bounds__(256) slab_pack2_kernel(const T* __restrict__ q
       for (int c = 0; c < stride; c++) out_q_hi[p * stride + c] = q[i * stride + c];
       out_gid_hi[p] = g;
     }
+  }
+}
+
+// Both faces of a slab in ONE kernel (nlb200_pack_faces): records with q[axis] < cut_lo go to the lo buffers, records
+// with q[axis] >= cut_hi to the hi buffers, positions from warp-aggregated atomics on two cursors (the order of the
+// ghosts is whatever the warps arrive in: the build sorts a cell's particles by global id, so its rows do not depend
+// on it).  The last CTA to finish publishes the two counts, pads the unused slots up to `capacity` with NaN records
+// (absent ghosts) and zeroes the cursors and the ticket for the next call — no memset, no scan, no second launch.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_faces_kernel(const T* __restrict__ q, const int32_t* __restrict__ gids,
+                                                         int64_t n, int stride, int axis, double cut_lo, double cut_hi,
+                                                         T* __restrict__ out_q_lo, int32_t* __restrict__ out_gid_lo,
+                                                         T* __restrict__ out_q_hi, int32_t* __restrict__ out_gid_hi,
+                                                         int64_t capacity, unsigned long long* __restrict__ state,
+                                                         int64_t* __restrict__ out_counts) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool f_lo = false, f_hi = false;
+  if (i < n) {
+    const double v = (double)q[i * stride + axis];
+    f_lo = out_q_lo != nullptr && v < cut_lo;
+    f_hi = out_q_hi != nullptr && v >= cut_hi;
+  }
+#pragma unroll
+  for (int f = 0; f < 2; f++) {
+    const bool flag = f == 0 ? f_lo : f_hi;
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (m == 0u) continue;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&state[f], (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    const int64_t pos = (int64_t)base + __popc(m & ((1u << lane) - 1u));
+    if (flag && pos < capacity) {
+      T* oq = f == 0 ? out_q_lo : out_q_hi;
+      int32_t* og = f == 0 ? out_gid_lo : out_gid_hi;
+      for (int c = 0; c < stride; c++) oq[pos * stride + c] = q[i * stride + c];
+      og[pos] = gids != nullptr ? gids[i] : (int32_t)i;
+    }
+  }
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&state[2], 1ull) == (unsigned long long)gridDim.x - 1ull;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const long long c_lo = (long long)*reinterpret_cast<volatile unsigned long long*>(&state[0]);
+  const long long c_hi = (long long)*reinterpret_cast<volatile unsigned long long*>(&state[1]);
+  const T nan = (T)__longlong_as_double(0x7ff8000000000000ll);
+  // every component: an absent record must fail any later coordinate test (periodic images are built axis by axis)
+  if (out_q_lo != nullptr)
+    for (int64_t t = c_lo * stride + threadIdx.x; t < capacity * stride; t += blockDim.x) out_q_lo[t] = nan;
+  if (out_q_hi != nullptr)
+    for (int64_t t = c_hi * stride + threadIdx.x; t < capacity * stride; t += blockDim.x) out_q_hi[t] = nan;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out_counts[0] = c_lo;
+    out_counts[1] = c_hi;
+    state[0] = state[1] = state[2] = 0ull;
   }
 }
 

@@ -38,17 +38,6 @@ constexpr int RM_ROWCAP = 128;  // rows of a cell staged per round
 #define NLB_RM_MINB 4
 #endif
 
-constexpr uint32_t FLAG_MASK_WORDS = 32u;  // the row-mask buffer is too small (status.mask_words tells the need)
-
-// What the emission needs to know about a cell, written by the row-mask kernel.
-struct alignas(8) CellRec {
-  int2 run[9];  // .x: end (exclusive) of run r in the cell's candidate list; .y: first slot of run r minus its start
-                //     in the list, so that slot = candidate index + .y.  Absent runs: .x = nj.
-  int32_t nj;         // candidates of the cell (length of the list)
-  int32_t self_base;  // candidate index of the cell's own first particle
-  unsigned long long mask_base;  // first word of the cell's block: word (k, i) at mask_base + k * n_A + i
-};
-
 struct RmDesc {
   int32_t cell, n_a, slot_a0, nj, self_base, nruns;
   unsigned long long mask_base;
@@ -281,9 +270,9 @@ __global__ void __launch_bounds__(RM_THREADS, NLB_RM_MINB) rowmask_kernel(RowMas
       d.nj = nj;
       d.self_base = self_base;
       d.nruns = nruns;
-      d.ox = ((float)cx + 0.5f) * msx;
-      d.oy = ((float)cy + 0.5f) * msy;
-      d.oz = ((float)cz + 0.5f) * msz;
+      d.ox = ((float)(cx + gp.coff[0]) + 0.5f) * msx;
+      d.oy = ((float)(cy + gp.coff[1]) + 0.5f) * msy;
+      d.oz = ((float)(cz + gp.coff[2]) + 0.5f) * msz;
     }
     if (n_a == 0) return;
     CellRec& cr = a.cellrec[cell];
@@ -558,6 +547,375 @@ __global__ void __launch_bounds__(RM_THREADS, NLB_RM_MINB) rowmask_kernel(RowMas
   if (warp == 0 && lane == 0) {
     if (cand_local) atomicAdd(&a.st->candidates, cand_local);
   }
+  if (band_local) atomicAdd(&a.st->band_tests, band_local);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// rowmask4_kernel — the same search with WARP-AUTONOMOUS units.
+// Profile of rowmask_kernel (profiles/r02_ncu_rowmask_v3a.txt): the main loop is 54 % of the instructions but 20 % of
+// the stall samples; 36 % of the samples sit at the three CTA barriers a cell costs (rows staged -> chunks done ->
+// counts written), with the four warps of a CTA in lock step per cell and warp 0 alone feeding the pipeline.
+// Here a unit is (cell, part): ONE warp takes the part's 32 * RJ candidates of the cell's list against all rows of the
+// cell and shares nothing with other warps — no CTA barrier exists.  Every warp runs its own three-deep pipeline:
+// ticket of the unit three ahead (atomic in flight), CellRec + cell bounds of the unit two ahead (loads in flight),
+// window piece + rows of the next unit by TMA into the warp's second buffer (mbarrier per buffer), compute the current
+// one.  The CellRec (run table, list length, mask block) is written by cellsort_kernel, which already has a warp per
+// cell, so the units of a cell agree on the block without talking to each other; row lengths accumulate with global
+// atomics (zeroed by cellsort_kernel).  Cells with more candidates than UPC parts cover, or more rows than RM4_ROWCAP,
+// loop inside the unit (later chunks / row rounds fetched synchronously).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RM4_ROWCAP = 64;  // rows staged per round
+struct Rm4Desc {
+  int32_t n_a, slot_a0, nj, self_base, part, pad0;
+  unsigned long long mask_base;
+  float ox, oy, oz;
+  int32_t pad1;
+  int32_t s0[9], cs[9], ce[9];  // first slot, start and end in the candidate list of run r
+  int32_t pad2;
+};
+template <int RJ>
+struct Rm4Smem {
+  float4 win[2][32 * RJ];
+  float4 rowraw[2][RM4_ROWCAP];
+  float4 srow[RM4_ROWCAP][2];
+  int32_t sid[RM4_ROWCAP];
+  int32_t scmp[RM4_ROWCAP];
+  Rm4Desc desc[2];
+  unsigned long long bars[2];
+};
+
+template <typename T>
+struct RowMask4Args {
+  const T* q;  // caller's positions (band re-test only)
+  GridParams<T> gp;
+  const int32_t* cell_start;
+  const float4* rec;          // cell-sorted records: absolute FP32 coordinates, .w = local id
+  const int32_t* global_ids;  // HALFMODE 2: local -> global id map
+  int32_t n_owned;
+  uint32_t* mask;
+  unsigned long long mask_cap;  // words
+  const CellRec* cellrec;
+  int32_t* counts;  // zeroed by cellsort_kernel
+  FastDiv d_mx, d_my, d_upc;
+  float band;
+  int32_t upc;      // parts (units) per cell
+  unsigned int* queue;
+  DeviceStatus* st;
+};
+
+template <typename T, int STRIDE, int HALFMODE, int RJ>
+__global__ void __launch_bounds__(RM_THREADS, NLB_RM_MINB) rowmask4_kernel(RowMask4Args<T> a) {
+  pdl_enter();
+  extern __shared__ __align__(128) unsigned char rm4_smem[];
+  constexpr int CH = 32 * RJ;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  Rm4Smem<RJ>& sm = reinterpret_cast<Rm4Smem<RJ>*>(rm4_smem)[warp];
+  const GridParams<T>& gp = a.gp;
+  const int32_t mx = gp.mesh[0], my = gp.mesh[1];
+  const float msx = gp.msf[0], msy = gp.msf[1], msz = gp.msf[2];
+  const TransposeConsts tc = make_transpose_consts(lane);
+  unsigned long long band_local = 0, cand_local = 0;
+  const unsigned int n_units = (unsigned int)gp.n_cells * (unsigned int)a.upc;  // < 2^31 (checked on the host)
+
+  if (lane == 0) {
+    mbar_init(&sm.bars[0], 1);
+    mbar_init(&sm.bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  // ---- per-warp pipeline state ----
+  const unsigned int n_warps = gridDim.x * RM_WARPS, gwarp = blockIdx.x * RM_WARPS + warp;
+  unsigned int u_cur = gwarp;                                            // position n
+  unsigned int u_nx1 = u_cur < n_units ? min(u_cur + n_warps, n_units) : n_units;  // n+1
+  unsigned int u_nx2 = u_nx1 < n_units ? min(u_nx1 + n_warps, n_units) : n_units;  // n+2
+  unsigned int q_pending = 0;   // ticket of position n+3 (lane 0; atomic in flight)
+  int32_t pf_x = 0, pf_y = 0;   // CellRec / cell bounds of position n+1 (lane-distributed, see issue_loads)
+  int32_t pf2_x = 0, pf2_y = 0; // ... of position n+2 (loads in flight)
+  uint32_t phases = 0u;
+
+  // lane r < 9: run[r]; lane 9: {nj, self_base}; lane 10: mask_base; lane 11: {cell_start[cell], cell_start[cell+1]}
+  auto issue_loads = [&](unsigned int u, int32_t& x, int32_t& y) {
+    x = 0;
+    y = 0;
+    if (u >= n_units) return;
+    const int32_t cell = (int32_t)fdiv(u, a.d_upc);
+    const int32_t* crw = reinterpret_cast<const int32_t*>(a.cellrec + cell);  // 22 words
+    if (lane < 11) {
+      const int2 v = __ldg(reinterpret_cast<const int2*>(crw) + lane);
+      x = v.x;
+      y = v.y;
+    } else if (lane == 11) {
+      x = __ldg(a.cell_start + cell);
+      y = __ldg(a.cell_start + cell + 1);
+    }
+  };
+  // descriptor of unit u in sm.desc[b] (scalars by lane 0, run values by lanes 0..8) + TMA fetch of its first chunk
+  // and first row round into buffer b
+  auto make_unit = [&](unsigned int u, int b, int32_t x, int32_t y) {
+    Rm4Desc& d = sm.desc[b];
+    __syncwarp();  // the previous reader of this descriptor is done
+    if (lane == 0) d.n_a = 0;
+    if (u >= n_units) return;
+    const int32_t cell = (int32_t)fdiv(u, a.d_upc);
+    const int32_t part = (int32_t)u - cell * a.upc;
+    const int32_t a0 = __shfl_sync(0xffffffffu, x, 11), a1 = __shfl_sync(0xffffffffu, y, 11);
+    const int32_t n_a = a1 - a0;
+    if (n_a == 0) return;  // warp-uniform
+    const int32_t nj = __shfl_sync(0xffffffffu, x, 9);
+    if (part * CH >= nj) return;  // this part has no chunk of the list
+    const int32_t self_base = __shfl_sync(0xffffffffu, y, 9);
+    const uint32_t mlo = (uint32_t)__shfl_sync(0xffffffffu, x, 10), mhi = (uint32_t)__shfl_sync(0xffffffffu, y, 10);
+    const int32_t cyz = (int32_t)fdiv((uint32_t)cell, a.d_mx), cx = cell - cyz * mx;
+    const int32_t cz = (int32_t)fdiv((uint32_t)cyz, a.d_my), cy = cyz - cz * my;
+    // run r: [cs, ce) in the list, first slot s0 = cs + delta
+    const int32_t prev_end = __shfl_up_sync(0xffffffffu, x, 1);
+    const int32_t ce = lane < 9 ? x : 0;
+    const int32_t cs = lane < 9 ? (lane == 0 ? 0 : prev_end) : 0;
+    const int32_t s0 = cs + y;
+    if (lane < 9) {
+      d.s0[lane] = s0;
+      d.cs[lane] = cs;
+      d.ce[lane] = ce;
+    }
+    if (lane == 0) {
+      d.n_a = n_a;
+      d.slot_a0 = a0;
+      d.nj = nj;
+      d.self_base = self_base;
+      d.part = part;
+      d.mask_base = ((unsigned long long)mhi << 32) | mlo;
+      d.ox = ((float)(cx + gp.coff[0]) + 0.5f) * msx;
+      d.oy = ((float)(cy + gp.coff[1]) + 0.5f) * msy;
+      d.oz = ((float)(cz + gp.coff[2]) + 0.5f) * msz;
+      if (part == 0) cand_local += (unsigned long long)n_a * (unsigned long long)nj;
+    }
+    rm_fetch(a.rec, sm.win[b], sm.rowraw[b], &sm.bars[b], lane, s0, cs, ce, part * CH, min(nj, part * CH + CH), a0, 0,
+             min(n_a, RM4_ROWCAP));
+  };
+
+  {
+    // prologue: position 0 synchronously, position 1's loads in flight
+    int32_t x, y;
+    issue_loads(u_cur, x, y);
+    make_unit(u_cur, 0, x, y);
+    issue_loads(u_nx1, pf_x, pf_y);
+    if (lane == 0) q_pending = atomicAdd(a.queue, 1u);
+    __syncwarp();
+  }
+
+  for (int n = 0; u_cur < n_units; n++) {
+    const int b = n & 1;
+    // position n+1: unit + TMA fetch into the other buffer (this warp finished its previous user, position n-1);
+    // position n+2: loads in flight until the next iteration
+    make_unit(u_nx1, b ^ 1, pf_x, pf_y);
+    issue_loads(u_nx2, pf2_x, pf2_y);
+    __syncwarp();
+    const Rm4Desc& d = sm.desc[b];
+    const int32_t n_a = d.n_a;
+    if (n_a > 0) {
+      const int32_t nj = d.nj, self_base = d.self_base, slot_a0 = d.slot_a0, part = d.part;
+      const float ox = d.ox, oy = d.oy, oz = d.oz;
+      float4* win = sm.win[b];
+      float4* rowraw = sm.rowraw[b];
+      const unsigned long long need = (unsigned long long)n_a * (unsigned long long)((nj + 31) >> 5);
+      const bool store = d.mask_base + need <= a.mask_cap;  // else FLAG_MASK_WORDS was raised by cellsort_kernel
+      uint32_t* mcell = a.mask + d.mask_base;
+      bool fetched = true;  // the prefetched first chunk + first row round are (still) in the buffers
+      for (int32_t rr = 0; rr < n_a; rr += RM4_ROWCAP) {
+        const int32_t nrows = min(RM4_ROWCAP, n_a - rr);
+        for (int32_t c_lo = part * CH; c_lo < nj; c_lo += a.upc * CH) {
+          const int32_t ncand = min(CH, nj - c_lo);
+          const bool first_chunk = c_lo == part * CH;
+          if (!fetched) {
+            // later chunks / row rounds of a crowded cell: fetched synchronously into the same buffer
+            __syncwarp();
+            rm_fetch(a.rec, win, rowraw, &sm.bars[b], lane, lane < 9 ? d.s0[lane] : 0, lane < 9 ? d.cs[lane] : 0,
+                     lane < 9 ? d.ce[lane] : 0, c_lo, c_lo + ncand, slot_a0, first_chunk ? rr : 0,
+                     first_chunk ? rr + nrows : 0);
+          }
+          mbar_wait(&sm.bars[b], (phases >> b) & 1u);
+          phases ^= 1u << b;
+          fetched = false;
+          if (first_chunk) {
+            // stage the round's rows: frame of the cell's centre, pre-duplicated for the packed FMAs
+            for (int32_t r = lane; r < nrows; r += 32) {
+              const float4 v = rowraw[r];
+              const float x = v.x - ox, y = v.y - oy, z = v.z - oz;
+              const float nai = -0.5f * (fmaf(x, x, fmaf(y, y, z * z)) - gp.sl2f);
+              sm.srow[r][0] = make_float4(x, x, y, y);
+              sm.srow[r][1] = make_float4(z, z, nai, nai);
+              const int32_t id = __float_as_int(v.w);
+              sm.sid[r] = id;
+              if (HALFMODE == 2) sm.scmp[r] = __ldg(a.global_ids + id);
+              if (HALFMODE == 1) sm.scmp[r] = id;
+            }
+            __syncwarp();
+          }
+          // ---- the chunk's candidates: RJ per lane, shifted into the cell's frame ----
+          float xj[RJ], yj[RJ], zj[RJ], wj[RJ];
+          int32_t cj[RJ];   // HALF: id the rule compares for candidate k
+          int32_t cut[RJ];  // HALFMODE 1: rows of the round with an id below the candidate's (a prefix)
+#pragma unroll
+          for (int k = 0; k < RJ; k++) {
+            const int32_t c = k * 32 + lane;
+            const float4 v = win[min(c, ncand - 1)];
+            xj[k] = v.x - ox;
+            yj[k] = v.y - oy;
+            zj[k] = v.z - oz;
+            wj[k] = -0.5f * fmaf(xj[k], xj[k], fmaf(yj[k], yj[k], zj[k] * zj[k]));
+            cj[k] = __float_as_int(v.w);
+            if (c >= ncand) {
+              xj[k] = yj[k] = zj[k] = 0.f;
+              wj[k] = -1.0e30f;  // d = -1e30: a miss, far from the band
+              cj[k] = 0x80000000;
+            } else if (HALFMODE == 2) {
+              cj[k] = __ldg(a.global_ids + cj[k]);
+            }
+            cut[k] = 0;
+          }
+          if (HALFMODE == 1) {
+            // rows keep partners with a LARGER id (neighlist_cpu.hpp:225-236): seen from candidate j, the rows with
+            // id_i < id_j — a prefix of the round, ids ascend with the slot inside a cell.  Lower bound over the
+            // staged ids, branch-free, the RJ searches interleaved
+            for (int32_t step = 1 << (31 - __clz(nrows)); step > 0; step >>= 1) {
+#pragma unroll
+              for (int k = 0; k < RJ; k++) {
+                const int32_t t = cut[k] + step;
+                if (t <= nrows && sm.scmp[min(t, nrows) - 1] < cj[k]) cut[k] = t;
+              }
+            }
+          }
+          f32x2 X[RJ / 2], Y[RJ / 2], Z[RJ / 2], W[RJ / 2];
+#pragma unroll
+          for (int h = 0; h < RJ / 2; h++) {
+            X[h] = pack2(xj[2 * h], xj[2 * h + 1]);
+            Y[h] = pack2(yj[2 * h], yj[2 * h + 1]);
+            Z[h] = pack2(zj[2 * h], zj[2 * h + 1]);
+            W[h] = pack2(wj[2 * h], wj[2 * h + 1]);
+          }
+          const int32_t nblk = (ncand + 31) >> 5;  // blocks of this chunk that hold candidates
+          const int32_t kblk0 = c_lo >> 5;          // their index in the cell's list
+          for (int32_t w = 0; w * 32 < nrows; w++) {
+            const int32_t cnt = min(32, nrows - w * 32);
+            const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(&sm.srow[w * 32][0]);
+            // rows are walked downwards so that row ii ends at bit ii; rows >= cnt keep the initial ones (= miss)
+            uint32_t miss[RJ];
+#pragma unroll
+            for (int k = 0; k < RJ; k++) miss[k] = 0xffffffffu;
+            float mh[RJ / 2];  // min |d| per candidate pair
+#pragma unroll
+            for (int h = 0; h < RJ / 2; h++) mh[h] = 3.0e38f;
+#pragma unroll 2
+            for (int32_t ii = cnt - 1; ii >= 0; ii--) {
+              const ulonglong2 p0 = sp[2 * ii];      // {xi, xi}, {yi, yi}
+              const ulonglong2 p1 = sp[2 * ii + 1];  // {zi, zi}, {-ai, -ai}
+#pragma unroll
+              for (int h = 0; h < RJ / 2; h++) {
+                const f32x2 d2 = add2(fma2(p0.x, X[h], fma2(p0.y, Y[h], fma2(p1.x, Z[h], W[h]))), p1.y);
+                float d0, d1;
+                unpack2(d2, d0, d1);
+                miss[2 * h] = __funnelshift_l(__float_as_uint(d0), miss[2 * h], 1);  // shift the sign bit in
+                miss[2 * h + 1] = __funnelshift_l(__float_as_uint(d1), miss[2 * h + 1], 1);
+                mh[h] = fminf(mh[h], fminf(fabsf(d0), fabsf(d1)));
+              }
+            }
+            uint32_t hits[RJ];
+#pragma unroll
+            for (int k = 0; k < RJ; k++) hits[k] = ~miss[k];  // bit ii <-> row w*32 + ii
+            // tests inside the pre-filter's uncertainty band are decided exactly, in the caller's precision, by the
+            // whole warp (lane = row, the triggering lane's candidate broadcast)
+            float mall = mh[0];
+#pragma unroll
+            for (int h = 1; h < RJ / 2; h++) mall = fminf(mall, mh[h]);
+            unsigned trig = __ballot_sync(0xffffffffu, mall < a.band);
+            while (trig) {
+              const int src = __ffs(trig) - 1;
+              trig &= trig - 1;
+#pragma unroll
+              for (int h = 0; h < RJ / 2; h++) {
+                if (!(__shfl_sync(0xffffffffu, mh[h], src) < a.band)) continue;  // warp-uniform
+                const f32x2 xs = __shfl_sync(0xffffffffu, X[h], src), ys = __shfl_sync(0xffffffffu, Y[h], src);
+                const f32x2 zs = __shfl_sync(0xffffffffu, Z[h], src), ws = __shfl_sync(0xffffffffu, W[h], src);
+                float cx2[2], cy2[2], cz2[2], cw2[2];
+                unpack2(xs, cx2[0], cx2[1]);
+                unpack2(ys, cy2[0], cy2[1]);
+                unpack2(zs, cz2[0], cz2[1]);
+                unpack2(ws, cw2[0], cw2[1]);
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                  const int k = 2 * h + e;
+                  const int32_t c_src = k * 32 + src;
+                  bool fix = false, hit = false;
+                  if (lane < cnt && c_src < ncand) {
+                    const float4 q0 = sm.srow[w * 32 + lane][0], q1 = sm.srow[w * 32 + lane][1];
+                    const float dd = pre_d(q0.x, q0.z, q1.x, q1.z, cx2[e], cy2[e], cz2[e], cw2[e]);
+                    if (fabsf(dd) < a.band) {
+                      const int32_t iid = sm.sid[w * 32 + lane];
+                      const int32_t jid = __float_as_int(win[c_src].w);
+                      hit = exact_within(load_pos<T, STRIDE>(a.q, iid), load_pos<T, STRIDE>(a.q, jid), gp.sl2);
+                      fix = true;
+                      band_local++;
+                    }
+                  }
+                  const uint32_t fixm = __ballot_sync(0xffffffffu, fix);  // lane ii <-> bit ii
+                  const uint32_t hitm = __ballot_sync(0xffffffffu, hit);
+                  if (lane == src) hits[k] = (hits[k] & ~fixm) | hitm;
+                }
+              }
+            }
+            if (HALFMODE == 1) {
+#pragma unroll
+              for (int k = 0; k < RJ; k++) {
+                const int32_t keep = cut[k] - w * 32;  // rows w*32 .. w*32 + keep - 1 have an id below the candidate's
+                hits[k] = keep <= 0 ? 0u : (keep >= 32 ? hits[k] : (hits[k] & ((1u << keep) - 1u)));
+              }
+            }
+            if (HALFMODE == 2) {
+              // ids are not monotone in the slot when they come from a map: compare per set bit
+#pragma unroll
+              for (int k = 0; k < RJ; k++) {
+                uint32_t m = hits[k];
+                while (m) {
+                  const int bpos = __ffs(m) - 1;
+                  m &= m - 1;
+                  if (!(cj[k] > sm.scmp[w * 32 + bpos])) hits[k] &= ~(1u << bpos);
+                }
+              }
+            }
+            // lane = candidate, bit = row   ->   lane = row, bit = candidate
+            const int32_t rg = rr + w * 32 + lane;  // this lane's row inside the cell
+            const int32_t cself = self_base + rg;   // ... and its own position in the candidate list (FULL: j != i)
+            const int32_t rid = sm.sid[min(w * 32 + lane, nrows - 1)];
+            const bool owned = lane < cnt && rid < a.n_owned;
+            int32_t pc = 0;
+#pragma unroll
+            for (int k = 0; k < RJ; k++) {
+              if (k < nblk) {
+                uint32_t t = transpose32(hits[k], tc);
+                if (HALFMODE == 0 && (cself >> 5) == kblk0 + k) t &= ~(1u << (cself & 31));
+                pc += __popc(t);
+                if (owned && store) mcell[(size_t)(kblk0 + k) * (size_t)n_a + (size_t)rg] = t;
+              }
+            }
+            if (owned && pc) atomicAdd(a.counts + rid, pc);
+          }
+        }
+        fetched = false;
+      }
+    }
+    // shift the pipeline: the ticket requested an iteration ago names position n+3
+    const unsigned int t = __shfl_sync(0xffffffffu, q_pending, 0);
+    if (lane == 0) q_pending = atomicAdd(a.queue, 1u);
+    const unsigned long long nxt = 3ull * n_warps + t;
+    u_cur = u_nx1;
+    u_nx1 = u_nx2;
+    u_nx2 = nxt < n_units ? (unsigned int)nxt : n_units;
+    pf_x = pf2_x;
+    pf_y = pf2_y;
+    __syncwarp();
+  }
+  if (cand_local) atomicAdd(&a.st->candidates, cand_local);
   if (band_local) atomicAdd(&a.st->band_tests, band_local);
 }
 

@@ -17,7 +17,8 @@ import torch
 
 from . import _lib
 from ._lib import (F32, F64, FULL_CSR, FULL_ELL_TRANSPOSED, HALF_CSR, OPT_ELL_ROWS, OPT_EXACT_ONLY,
-                   OPT_KERNEL_VARIANT, OPT_MAX_IN_CELL, OPT_POSITION_STRIDE, OPT_PROFILE, OPT_SORT_ROWS, OPT_USE_GRAPH, NlistError,
+                   OPT_KERNEL_VARIANT, OPT_MAX_IN_CELL, OPT_PDL, OPT_POSITION_STRIDE, OPT_PROFILE, OPT_SORT_ROWS,
+                   OPT_USE_GRAPH, NlistError,
                    Stats, check)
 
 _MODES = {"half_csr": HALF_CSR, "full_csr": FULL_CSR, "full_ell_transposed": FULL_ELL_TRANSPOSED}
@@ -43,7 +44,8 @@ class VerletListB200:
 
     def __init__(self, search_length: float, Lx: float, Ly: float, Lz: float, dtype="f64", mode="full_csr",
                  position_stride: int = 4, sort_rows: bool = False, ell_rows: int = 200, exact_only: bool = False,
-                 use_graph: bool = True, kernel_variant: int = 0, profile: bool = False, max_in_cell: int = 0):
+                 use_graph: bool = True, kernel_variant: int = 0, profile: bool = False, max_in_cell: int = 0,
+                 cell_window=None, pdl: bool | None = None):
         self._lib = _lib.lib()
         self._h = C.c_void_p()
         self.dtype = _DTYPES[dtype]
@@ -58,6 +60,12 @@ class VerletListB200:
                          (OPT_USE_GRAPH, int(use_graph)), (OPT_KERNEL_VARIANT, int(kernel_variant)),
                          (OPT_PROFILE, int(profile)), (OPT_MAX_IN_CELL, int(max_in_cell))):
             check(self._h, self._lib.nlb200_set_option(self._h, opt, val))
+        if pdl is not None:
+            check(self._h, self._lib.nlb200_set_option(self._h, OPT_PDL, int(pdl)))
+        if cell_window is not None:
+            # (axis, first_cell, n_cells): this handle bins only that window of the global grid (a slab rank)
+            axis, first, count = cell_window
+            check(self._h, self._lib.nlb200_set_cell_window(self._h, int(axis), int(first), int(count)))
         self.n = 0
         self.device = None
         self._q_keepalive = None

@@ -15,13 +15,15 @@ The ghost buffers have a FIXED capacity per face and unused slots hold NaN recor
 (include/nlist_b200.h, nlb200_pack_slab): no rank has to learn a count before it posts its receive or launches its
 build, so an exchange + build is enqueued without a single host synchronisation and replays the library's CUDA graph.
 
-Every rank bins on the GLOBAL cell grid (the handle is created with the global box), so the rows it emits are exactly
-the rows a single-GPU build of the whole system would emit for those particles — same partners, same order.  HALF
+Every rank assigns cells on the GLOBAL cell grid (the handle is created with the global box), so the rows it emits are
+exactly the rows a single-GPU build of the whole system would emit for those particles — same partners, same order
+(a cell's particles are sorted by global id) — but bins, sorts and searches only its own WINDOW of that grid: the
+cells of its slab plus the ghost layer (`cell_window()`, nlb200_set_cell_window), not a grid that is mostly empty.  HALF
 lists: the row of the smaller global id keeps the pair, so each pair is emitted once, by the rank that owns that
 particle (ghosts are needed from both faces).  Open boundary (the reference measures distances without minimum image,
 neighlist_cpu.hpp:219-223): the end slabs have one neighbour.
 
-Device path: selection, packing and padding run in the library's CUDA kernels (nlb200_pack_slab).  The same
+Device path: selection, packing and padding of both faces run in ONE kernel of the library (nlb200_pack_faces).  The same
 partition / exchange / ownership logic also accepts CPU tensors (torch ops + the `gloo` backend); that branch exists so
 that the world_size-2 tests can exercise the logic without GPUs — it is not a compute fallback: the list build itself
 is injected by the caller (`build_fn`) and is the CUDA library in the product.
@@ -53,10 +55,10 @@ class SlabDecomposition:
         self.group = group
         self.slack = float(slack)  # ghost capacity per face = expected count * slack + 1024
         self._cap = None
-        self._ws = None  # device workspace of nlb200_pack_slab
         self._qall = self._gall = self._sq = self._sg = self._cnt = self._cnt_host = None
         self._last = None
         self._gid_default = None
+        self._cnt2 = self._state = None
 
     # -- partitioning ---------------------------------------------------------------------------------------------
     def owns(self, q: np.ndarray) -> np.ndarray:
@@ -77,6 +79,24 @@ class SlabDecomposition:
         q = workloads.fcc(density, L, seed=seed + self.rank, stride=self.stride)
         q[:, self.axis] += self.rank * self.thickness
         return q
+
+    def cell_window(self):
+        """(axis, first_cell, n_cells): the cells of the global grid this rank can hold particles in — its slab plus one
+        search length of ghosts on either side, plus one cell of slack for the rounding of int(q * ims) — for
+        VerletListB200(..., cell_window=...).  None on one rank."""
+        if self.world == 1:
+            return None
+        m = int(self.box[self.axis] / self.sl)  # neighlist_cpu.hpp:384-387
+        ms = self.box[self.axis] / m
+        lo = 0 if self.rank == 0 else int((self.lo - self.sl) / ms) - 1
+        hi = m - 1 if self.rank + 1 == self.world else int((self.hi + self.sl) / ms) + 1
+        lo, hi = max(lo, 0), min(hi, m - 1)
+        if hi - lo + 1 == 3 and m > 3:  # a window of exactly 3 cells would be taken for a 3-cell (wrapped) axis
+            if hi + 1 < m:
+                hi += 1
+            else:
+                lo -= 1
+        return (self.axis, lo, hi - lo + 1)
 
     def n_faces(self) -> int:
         return (1 if self.rank > 0 else 0) + (1 if self.rank + 1 < self.world else 0)
@@ -107,7 +127,7 @@ class SlabDecomposition:
               out_g: torch.Tensor, count: torch.Tensor) -> None:
         """out_q/out_g[0:k] = the records / global ids with lo <= q[:, axis] < hi (ascending), NaN records behind;
         count[0] = k (may exceed the capacity: overflow, reported by check())."""
-        n, cap = q.shape[0], out_q.shape[0]
+        cap = out_q.shape[0]
         if not q.is_cuda:  # logic tests on CPU tensors (gloo); same contract as the CUDA kernels
             z = q[:, self.axis]
             idx = torch.nonzero((z >= lo) & (z < hi)).flatten()
@@ -117,16 +137,7 @@ class SlabDecomposition:
             out_q[:idx.numel()] = q[idx]
             out_g[:idx.numel()] = gid[idx]
             return
-        L = _lib.lib()
-        ws_bytes = L.nlb200_select_slab_workspace(n)
-        if self._ws is None or self._ws.numel() < ws_bytes:
-            self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
-        dtype = _lib.F64 if q.dtype == torch.float64 else _lib.F32
-        st = L.nlb200_pack_slab(q.data_ptr(), gid.data_ptr(), 0, n, dtype, self.stride, self.axis, lo, hi,
-                                out_q.data_ptr(), out_g.data_ptr(), cap, count.data_ptr(), self._ws.data_ptr(),
-                                ws_bytes, torch.cuda.current_stream().cuda_stream)
-        if st != _lib.OK:
-            raise _lib.NlistError(st, "nlb200_pack_slab failed")
+        raise RuntimeError("CUDA tensors are packed by nlb200_pack_faces (exchange), not here")
 
     def _alloc(self, n_total, cap, peers, dtype, dev):
         # persistent buffers: stable device pointers and sizes, so identical builds replay the library's CUDA graph
@@ -157,23 +168,21 @@ class SlabDecomposition:
             self._gall[:n].copy_(gid_owned)
         lo_p, hi_p = self.rank - 1, self.rank + 1
         if q_owned.is_cuda:
-            # both faces in one pass over the positions (nlb200_pack_slab2)
+            # both faces in one kernel launch (nlb200_pack_faces)
             L = _lib.lib()
-            ws_bytes = 2 * L.nlb200_select_slab_workspace(n) + 512
-            if self._ws is None or self._ws.numel() < ws_bytes:
-                self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            if self._state is None or self._state.device != dev:
+                self._state = torch.zeros(4, dtype=torch.int64, device=dev)  # zeroed once: the kernel leaves it zeroed
                 self._cnt2 = torch.zeros(2, dtype=torch.int64, device=dev)
             dtype = _lib.F64 if q_owned.dtype == torch.float64 else _lib.F32
             has_lo, has_hi = lo_p in self._sq, hi_p in self._sq
-            st = L.nlb200_pack_slab2(
+            st = L.nlb200_pack_faces(
                 q_owned.data_ptr(), gid_owned.data_ptr(), n, dtype, self.stride, self.axis,
                 self.lo + self.sl if has_lo else -float("inf"), self.hi - self.sl if has_hi else float("inf"),
                 self._sq[lo_p].data_ptr() if has_lo else None, self._sg[lo_p].data_ptr() if has_lo else None,
                 self._sq[hi_p].data_ptr() if has_hi else None, self._sg[hi_p].data_ptr() if has_hi else None,
-                cap, self._cnt2.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
-                torch.cuda.current_stream().cuda_stream)
+                cap, self._cnt2.data_ptr(), self._state.data_ptr(), torch.cuda.current_stream().cuda_stream)
             if st != _lib.OK:
-                raise _lib.NlistError(st, "nlb200_pack_slab2 failed")
+                raise _lib.NlistError(st, "nlb200_pack_faces failed")
             if has_lo:
                 self._cnt[lo_p] = self._cnt2[0:1]
             if has_hi:

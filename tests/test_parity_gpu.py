@@ -475,6 +475,86 @@ def test_absent_ghost_slots_and_halo_packing(cuda, oracle):
             assert np.array_equal(lst[off[li]:off[li + 1]], want)
 
 
+def test_cell_window_and_single_kernel_packing(cuda, oracle):
+    """What a slab rank does (parallel.py): both faces packed by ONE kernel (nlb200_pack_faces: unordered, NaN padded),
+    and a handle that bins only its WINDOW of the global grid (nlb200_set_cell_window) — the rows must equal the rows
+    of a single build of the whole system, whatever order the ghosts arrive in."""
+    import ctypes as C
+    from md_neighbor_list_b200 import VerletListB200, _lib, workloads
+    torch = cuda
+    L, SL = 40.0, 3.3
+    q = workloads.fcc(1.0, L)
+    n = q.shape[0]
+    Lb = _lib.lib()
+    # --- packing: records below cut_lo / at or above cut_hi, any order, NaN behind, counts exact ---
+    qd = torch.from_numpy(q).cuda()
+    gids = (torch.arange(n, dtype=torch.int32, device="cuda") * 3 + 7)
+    cap = 20000
+    out_q = [torch.zeros((cap, 4), dtype=torch.float64, device="cuda") for _ in range(2)]
+    out_g = [torch.zeros(cap, dtype=torch.int32, device="cuda") for _ in range(2)]
+    cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+    state = torch.zeros(4, dtype=torch.int64, device="cuda")
+    for rep in range(2):  # the kernel leaves its state zeroed: a second call needs no reset
+        st = Lb.nlb200_pack_faces(qd.data_ptr(), gids.data_ptr(), n, _lib.F64, 4, 2, 3.3, L - 3.3, out_q[0].data_ptr(),
+                                  out_g[0].data_ptr(), out_q[1].data_ptr(), out_g[1].data_ptr(), cap, cnt.data_ptr(),
+                                  state.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert st == _lib.OK
+        torch.cuda.synchronize()
+        assert int(state.abs().sum()) == 0
+        for f, sel in ((0, np.nonzero(q[:, 2] < 3.3)[0]), (1, np.nonzero(q[:, 2] >= L - 3.3)[0])):
+            k = int(cnt[f])
+            assert k == len(sel) and 0 < k < cap
+            got_g = out_g[f][:k].cpu().numpy()
+            order = np.argsort(got_g)
+            assert np.array_equal(got_g[order], (sel * 3 + 7).astype(np.int32))
+            assert np.array_equal(out_q[f][:k].cpu().numpy()[order], q[sel])
+            assert np.isnan(out_q[f][k:].cpu().numpy()).all()
+    # --- window: the middle slab of three, ghosts from both faces in SHUFFLED order, absent slots in between ---
+    lo, hi = L / 3, 2 * L / 3
+    own = np.nonzero((q[:, 2] >= lo) & (q[:, 2] < hi))[0]
+    gh = np.nonzero(((q[:, 2] >= lo - SL) & (q[:, 2] < lo)) | ((q[:, 2] >= hi) & (q[:, 2] < hi + SL)))[0]
+    gh = np.random.default_rng(3).permutation(gh)
+    pad = 300
+    q_all = np.full((len(own) + len(gh) + pad, 4), np.nan)
+    q_all[:len(own)] = q[own]
+    g_all = np.zeros(len(q_all), dtype=np.int32)
+    g_all[:len(own)] = own
+    slots = len(own) + np.sort(np.random.default_rng(4).choice(len(gh) + pad, len(gh), replace=False))
+    q_all[slots] = q[gh]
+    g_all[slots] = gh
+    m = int(L / SL)
+    ms = L / m
+    first, last = int((lo - SL) / ms) - 1, int((hi + SL) / ms) + 1
+    for mode, builder in (("full_csr", oracle.build_full), ("half_csr", oracle.build_half)):
+        ref = builder(q, SL, (L, L, L))
+        for variant in (0, 6):
+            nl = VerletListB200(SL, L, L, L, mode=mode, kernel_variant=variant, cell_window=(2, first, last - first + 1))
+            nl.initialize(len(q_all))
+            nl.build(torch.from_numpy(q_all).cuda(), n_owned=len(own), global_ids=torch.from_numpy(g_all).cuda())
+            st = nl.synchronize()
+            assert list(st.mesh) == [m, m, m]  # the statistics keep reporting the global grid
+            off = nl.offsets().cpu().numpy()
+            lst = nl.partners().cpu().numpy()
+            assert np.array_equal(nl.number_of_partners().cpu().numpy(), ref.number_of_partners[own])
+            for li in range(0, len(own), 7):
+                g = own[li]
+                want = ref.partners[ref.offsets[g]:ref.offsets[g + 1]]
+                if mode == "full_csr":
+                    # same ORDER as the single build: cells ascending, global ids ascending inside a cell
+                    assert np.array_equal(lst[off[li]:off[li + 1]], want)
+                else:
+                    assert np.array_equal(np.sort(lst[off[li]:off[li + 1]]), np.sort(want))
+            nl.close()
+    # a particle outside the window is reported
+    nl = VerletListB200(SL, L, L, L, cell_window=(2, 0, 4))
+    nl.initialize(n)
+    nl.build(qd)
+    from md_neighbor_list_b200 import NlistError
+    with pytest.raises(NlistError) as e:
+        nl.synchronize()
+    assert e.value.status == _lib.ERR_OUT_OF_BOX
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # full-size properties (BASELINE.json configs[2]: 16M uniform, density 1.0, SL 3.3)
 # ---------------------------------------------------------------------------------------------------------------
@@ -605,24 +685,86 @@ def test_cell_capacity_overflow_is_detected_then_recovered(cuda, oracle):
 @pytest.mark.parametrize("mode", ["full_csr", "half_csr"])
 def test_kernel_variants_emit_identical_lists(cuda, oracle, mode):
     """variant 1 = one CTA per cell, test evaluated twice; 2 = pair masks + staged emission; 3 = pair masks + direct
-    emission.  Same rows, same order (stencil order), same counts and offsets."""
+    emission; 5 = row masks, CTA per cell; 6 = row masks, warp-autonomous units (the path crowded cells take).  Same
+    rows, same order (stencil order), same counts and offsets."""
     from md_neighbor_list_b200 import workloads
     q = workloads.fcc(1.0, 23.0)
     box = (23.0, 23.0, 23.0)
     # 4 = HALF rows filtered by id during the emission (the multi-GPU path) instead of inside the masks
     # 7 = mask indices in 64-bit arithmetic (the path of systems whose masks exceed 2^32 words)
-    outs = [gpu_build(cuda, q, 3.3, box, mode, kernel_variant=v) for v in (1, 2, 3, 4, 7)]
+    outs = [gpu_build(cuda, q, 3.3, box, mode, kernel_variant=v) for v in (1, 2, 3, 4, 7, 5, 6, 0)]
     for o in outs[1:]:
         assert o["pairs"] == outs[0]["pairs"]
         assert np.array_equal(o["np"], outs[0]["np"])
         assert np.array_equal(o["off"], outs[0]["off"])
-    assert np.array_equal(outs[1]["list"], outs[2]["list"])
-    assert np.array_equal(outs[1]["list"], outs[3]["list"])
-    assert np.array_equal(outs[1]["list"], outs[4]["list"])
+    for o in outs[2:]:
+        assert np.array_equal(outs[1]["list"], o["list"])
     if mode == "full_csr":
         assert np.array_equal(outs[0]["list"], outs[1]["list"])
     ref = oracle.build_full(q, 3.3, box) if mode == "full_csr" else oracle.build_half(q, 3.3, box)
     assert_matches(oracle, outs[2], ref)
+    assert_matches(oracle, outs[6], ref)
+
+
+@pytest.mark.parametrize("variant", [5, 6])
+def test_row_mask_path_on_every_input_class(cuda, oracle, variant):
+    """The row-mask search (TMA-staged windows, transposed verdict blocks, per-cell mask blocks) on the input classes
+    that exercise its special cases: 3-cell axes (wrapped stencil cells are real neighbours), empty cells, cells of
+    more rows than one round stages, windows larger than one staged chunk, owned subsets with a global-id map, FP32
+    positions, pairs on the search radius."""
+    from md_neighbor_list_b200 import VerletListB200, workloads
+    torch = cuda
+    rng = np.random.default_rng(8)
+    box = (13.0, 29.5, 10.1)
+    q = np.zeros((5000, 4))
+    q[:, :3] = rng.random((5000, 3)) * np.array(box)
+    q[150:170, :3] = q[170:190, :3]  # duplicates: r2 == 0
+    for mode, full in (("full_csr", True), ("half_csr", False)):
+        got = gpu_build(cuda, q, 3.3, box, mode, kernel_variant=variant)
+        assert_matches(oracle, got, oracle.bruteforce(q, 3.3, full=full))
+    q = np.zeros((300, 4))
+    q[:, :3] = rng.random((300, 3)) * 60.0
+    got = gpu_build(cuda, q, 3.3, (60.0,) * 3, "full_csr", kernel_variant=variant)
+    assert_matches(oracle, got, oracle.bruteforce(q, 3.3, full=True))
+    q = workloads.clustered(12000, 30.0, blobs=4)
+    for mode, builder in (("full_csr", oracle.build_full), ("half_csr", oracle.build_half)):
+        got = gpu_build(cuda, q, 2.3, (30.0,) * 3, mode, kernel_variant=variant)
+        assert got["max_in_cell"] > 128
+        assert_matches(oracle, got, builder(q, 2.3, (30.0,) * 3))
+    qf = workloads.fcc(1.0, 30.0).astype(np.float32)
+    got = gpu_build(cuda, qf, 3.3, (30.0,) * 3, "full_csr", dtype="f32", kernel_variant=variant)
+    assert_matches(oracle, got, oracle.build_full(qf, 3.3, (30.0,) * 3))
+    # pairs within a few ulp of the search radius: the band re-test decides them exactly
+    SL, L, n0 = 3.3, 40.0, 3000
+    base = rng.random((n0, 3)) * (L - 8.0) + 4.0
+    dirs = rng.normal(size=(n0, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    q = np.zeros((2 * n0, 4))
+    q[:n0, :3] = base
+    q[n0:, :3] = base + dirs * (SL * (1.0 + rng.integers(-4, 5, size=(n0, 1)) * 2.0 ** -52))
+    got = gpu_build(cuda, q, SL, (L,) * 3, "full_csr", kernel_variant=variant)
+    assert got["band"] >= n0
+    assert_matches(oracle, got, oracle.build_full(q, SL, (L,) * 3))
+    # owned subset + global ids (HALF by global id: the per-bit comparison)
+    L = 24.0
+    q = workloads.fcc(1.0, L)
+    n = q.shape[0]
+    perm = rng.permutation(n).astype(np.int32)
+    n_owned = n // 3
+    ql = np.ascontiguousarray(q[perm])
+    for mode, builder in (("full_csr", oracle.build_full), ("half_csr", oracle.build_half)):
+        nl = VerletListB200(3.3, L, L, L, mode=mode, kernel_variant=variant)
+        nl.initialize(n)
+        nl.build(torch.from_numpy(ql).cuda(), n_owned=n_owned, global_ids=torch.from_numpy(perm).cuda())
+        nl.synchronize()
+        ref = builder(q, 3.3, (L, L, L)).sorted_rows()
+        off = nl.offsets().cpu().numpy()
+        lst = sort_rows(oracle, nl.partners().cpu().numpy(), off)
+        assert np.array_equal(nl.number_of_partners().cpu().numpy(), ref.number_of_partners[perm[:n_owned]])
+        for li in range(0, n_owned, 29):
+            g = perm[li]
+            assert np.array_equal(lst[off[li]:off[li + 1]], ref.partners[ref.offsets[g]:ref.offsets[g + 1]])
+        nl.close()
 
 
 def test_programmatic_dependent_launch_gives_the_same_list(cuda, oracle, monkeypatch):
