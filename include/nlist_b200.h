@@ -268,6 +268,37 @@ int nlb200_pack_faces(const void* q_dev, const int32_t* gids_dev, int64_t n, int
                       int32_t* out_gid_hi_dev, int64_t capacity, int64_t* out_counts_dev, void* state_dev,
                       void* stream);
 
+/* ---- halo exchange by peer stores: the packing kernel IS the transfer (no NCCL call on the step) ------------------
+ * A slab rank keeps its assembly buffer [owned | ghosts from below | ghosts from above] (and the matching global ids,
+ * and a 64-byte control block) in memory it allocates with nlb200_p2p_alloc; the 64-byte IPC handles are exchanged
+ * once through any host channel (the Python driver uses torch.distributed, a C++ host MPI or a file) and opened with
+ * nlb200_p2p_open.  Per step, on one stream:
+ *     nlb200_pack_faces_p2p   writes this rank's face particles INTO THE NEIGHBOURS' ghost regions over NVLink, pads
+ *                             the unused slots with NaN records, then raises the neighbours' `ready` flags;
+ *     nlb200_halo_wait        the ghosts of both faces have arrived (nlb200_pack_faces_p2p also waits for them before it
+ *                             ends: the call is only needed by a host that packs and builds on different streams);
+ *     nlb200_build_subset     the build;
+ *     nlb200_halo_done        tells the neighbours that their ghosts may be overwritten, advances the step counter.
+ * Flags carry a device-side step number (control block: u64 step, ready[2], free_from[2], error, pad[2]), so the four
+ * calls replay as a CUDA graph; every device-side wait is bounded (~1 s) and sets `error` instead of hanging.
+ * peer_ready_lo / peer_free_lo point at ready[1] / free_from[1] of the LOWER neighbour's control block (this rank is
+ * its upper face), peer_ready_hi / peer_free_hi at ready[0] / free_from[0] of the upper neighbour's; NULL = no such
+ * neighbour (end slab).  state_dev: 64 bytes of device memory zeroed once by the caller. */
+int nlb200_p2p_alloc(int64_t bytes, void** dev_ptr, void* ipc_handle_64);
+int nlb200_p2p_open(const void* ipc_handle_64, void** peer_ptr);
+int nlb200_p2p_close(void* peer_ptr);
+int nlb200_p2p_free(void* dev_ptr);
+int nlb200_pack_faces_p2p(const void* q_dev, const int32_t* gids_dev, int64_t n, int dtype, int stride, int axis,
+                          double cut_lo, double cut_hi, void* peer_q_lo, int32_t* peer_gid_lo, void* peer_q_hi,
+                          int32_t* peer_gid_hi, int64_t capacity, int64_t* out_counts_dev, void* state_dev,
+                          void* ctrl_dev, void* peer_ready_lo, void* peer_ready_hi, void* stream);
+int nlb200_halo_wait(void* ctrl_dev, int faces, void* stream);
+/* Folds nlb200_halo_done into the last kernel of every build of `h` (one launch less per step); NULL ctrl_dev undoes
+ * it.  nlb200_pack_faces_p2p already waits for this rank's own ghosts before it ends, so a step is two calls:
+ * nlb200_pack_faces_p2p, nlb200_build_subset. */
+int nlb200_set_halo_sync(nlb200_handle h, void* ctrl_dev, void* peer_free_lo, void* peer_free_hi);
+int nlb200_halo_done(void* ctrl_dev, void* peer_free_lo, void* peer_free_hi, void* stream);
+
 /* Bytes of workspace nlb200_select_slab / nlb200_pack_slab need for n particles. */
 int64_t nlb200_select_slab_workspace(int64_t n);
 

@@ -68,6 +68,15 @@ SYMBOLS = {
     "nlb200_pack_slab2": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64,
                                     _vp]),
     "nlb200_pack_faces": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "nlb200_p2p_alloc": (C.c_int, [_i64, C.POINTER(_vp), _vp]),
+    "nlb200_p2p_open": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "nlb200_p2p_close": (C.c_int, [_vp]),
+    "nlb200_p2p_free": (C.c_int, [_vp]),
+    "nlb200_pack_faces_p2p": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _i64, _vp, _vp,
+                                        _vp, _vp, _vp, _vp]),
+    "nlb200_halo_wait": (C.c_int, [_vp, _i32, _vp]),
+    "nlb200_set_halo_sync": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "nlb200_halo_done": (C.c_int, [_vp, _vp, _vp, _vp]),
     "nlb200_select_slab_workspace": (_i64, [_i64]),
     "nlb200_shift_axis": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _dbl, _vp]),
     "nlb200_gather_records": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),

@@ -50,6 +50,9 @@ struct nlb200_context {
   unsigned long long* queue = nullptr;  // work counter of the persistent pair-mask kernel (inside zero_region)
   unsigned int* ticket = nullptr;       // CTA ticket of bin_kernel's last-CTA scan (inside zero_region)
   size_t status_off = 0;                // byte offset of the status block inside zero_region
+  void* halo_ctrl = nullptr;            // nlb200_set_halo_sync: control block + the neighbours' free flags
+  void* halo_free_lo = nullptr;
+  void* halo_free_hi = nullptr;
   int path = 0;                         // PATH_*: which search / emission pair the handle runs (pick_path)
   bool state_clean = false;             // the zero region is all zero (left so by the last build's finalize_kernel)
   int sm_count = 148;
@@ -744,7 +747,9 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     if (fgrid > (unsigned)h->sm_count * 4) fgrid = (unsigned)h->sm_count * 4;
     CK(h, launch_chain(finalize_kernel, dim3(fgrid), dim3(256), 0, s, h->status_dev, h->status_host,
                        reinterpret_cast<uint4*>(h->zero_region), vecs, h->status_off / 16,
-                       (sizeof(DeviceStatus) + 15) / 16));
+                       (sizeof(DeviceStatus) + 15) / 16, reinterpret_cast<HaloCtrl*>(h->halo_ctrl),
+                       reinterpret_cast<unsigned long long*>(h->halo_free_lo),
+                       reinterpret_cast<unsigned long long*>(h->halo_free_hi)));
   }
   h->state_clean = true;
   if (h->profile) CK(h, cudaEventRecord(h->ev[h->n_stages], s));
@@ -1567,6 +1572,96 @@ int nlb200_pack_faces(const void* q_dev, const int32_t* gids_dev, int64_t n, int
     pack_faces_kernel<float><<<g, 256, 0, s>>>((const float*)q_dev, gids_dev, n, stride, axis, cut_lo, cut_hi,
                                               (float*)out_q_lo_dev, out_gid_lo_dev, (float*)out_q_hi_dev,
                                               out_gid_hi_dev, capacity, st, out_counts_dev);
+  return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
+}
+
+// ---- halo exchange by peer stores (CUDA IPC) ---------------------------------------------------------------------
+int nlb200_p2p_alloc(int64_t bytes, void** dev_ptr, void* ipc_handle_64) {
+  if (bytes <= 0 || !dev_ptr || !ipc_handle_64) return NLB200_ERR_INVALID;
+  (void)cudaGetLastError();
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  void* p = nullptr;
+  if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) return NLB200_ERR_CUDA;
+  if (cudaMemset(p, 0, (size_t)bytes) != cudaSuccess ||
+      cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(ipc_handle_64), p) != cudaSuccess) {
+    cudaFree(p);
+    (void)cudaGetLastError();
+    return NLB200_ERR_CUDA;
+  }
+  *dev_ptr = p;
+  return NLB200_OK;
+}
+
+int nlb200_p2p_open(const void* ipc_handle_64, void** peer_ptr) {
+  if (!ipc_handle_64 || !peer_ptr) return NLB200_ERR_INVALID;
+  (void)cudaGetLastError();
+  cudaIpcMemHandle_t hdl;
+  memcpy(&hdl, ipc_handle_64, sizeof(hdl));
+  if (cudaIpcOpenMemHandle(peer_ptr, hdl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return NLB200_ERR_CUDA;
+  }
+  return NLB200_OK;
+}
+
+int nlb200_p2p_close(void* peer_ptr) {
+  if (!peer_ptr) return NLB200_OK;
+  return cudaIpcCloseMemHandle(peer_ptr) == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
+}
+
+int nlb200_p2p_free(void* dev_ptr) {
+  if (!dev_ptr) return NLB200_OK;
+  return cudaFree(dev_ptr) == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
+}
+
+int nlb200_pack_faces_p2p(const void* q_dev, const int32_t* gids_dev, int64_t n, int dtype, int stride, int axis,
+                          double cut_lo, double cut_hi, void* peer_q_lo, int32_t* peer_gid_lo, void* peer_q_hi,
+                          int32_t* peer_gid_hi, int64_t capacity, int64_t* out_counts_dev, void* state_dev,
+                          void* ctrl_dev, void* peer_ready_lo, void* peer_ready_hi, void* stream) {
+  if (n < 0 || capacity < 0 || axis < 0 || axis > 2 || (stride != 3 && stride != 4) || !state_dev ||
+      !out_counts_dev || !ctrl_dev)
+    return NLB200_ERR_INVALID;
+  (void)cudaGetLastError();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned g = (unsigned)((n + 255) / 256 > 0 ? (n + 255) / 256 : 1);
+  unsigned long long* st = reinterpret_cast<unsigned long long*>(state_dev);
+  HaloCtrl* ctrl = reinterpret_cast<HaloCtrl*>(ctrl_dev);
+  unsigned long long* rl = reinterpret_cast<unsigned long long*>(peer_ready_lo);
+  unsigned long long* rh = reinterpret_cast<unsigned long long*>(peer_ready_hi);
+  if (dtype == NLB200_F64)
+    pack_faces_p2p_kernel<double><<<g, 256, 0, s>>>((const double*)q_dev, gids_dev, n, stride, axis, cut_lo, cut_hi,
+                                                   (double*)peer_q_lo, peer_gid_lo, (double*)peer_q_hi, peer_gid_hi,
+                                                   capacity, st, out_counts_dev, ctrl, rl, rh);
+  else
+    pack_faces_p2p_kernel<float><<<g, 256, 0, s>>>((const float*)q_dev, gids_dev, n, stride, axis, cut_lo, cut_hi,
+                                                  (float*)peer_q_lo, peer_gid_lo, (float*)peer_q_hi, peer_gid_hi,
+                                                  capacity, st, out_counts_dev, ctrl, rl, rh);
+  return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
+}
+
+int nlb200_set_halo_sync(nlb200_handle h, void* ctrl_dev, void* peer_free_lo, void* peer_free_hi) {
+  if (!h) return NLB200_ERR_INVALID;
+  if (h->build_pending && h->last_stream) CK(h, cudaStreamSynchronize(h->last_stream));
+  h->halo_ctrl = ctrl_dev;
+  h->halo_free_lo = ctrl_dev ? peer_free_lo : nullptr;
+  h->halo_free_hi = ctrl_dev ? peer_free_hi : nullptr;
+  drop_graph(h);  // the pointers are arguments of the captured finalize_kernel
+  return NLB200_OK;
+}
+
+int nlb200_halo_wait(void* ctrl_dev, int faces, void* stream) {
+  if (!ctrl_dev) return NLB200_ERR_INVALID;
+  (void)cudaGetLastError();
+  halo_wait_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<HaloCtrl*>(ctrl_dev), faces);
+  return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
+}
+
+int nlb200_halo_done(void* ctrl_dev, void* peer_free_lo, void* peer_free_hi, void* stream) {
+  if (!ctrl_dev) return NLB200_ERR_INVALID;
+  (void)cudaGetLastError();
+  halo_done_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<HaloCtrl*>(ctrl_dev), reinterpret_cast<unsigned long long*>(peer_free_lo),
+      reinterpret_cast<unsigned long long*>(peer_free_hi));
   return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
 }
 

@@ -1019,6 +1019,13 @@ __global__ void __launch_bounds__(PM_THREADS, NLB_PM_MINB) pairmask_kernel(PairM
             if (idj < a.n_owned) oj[k] = __float_as_int(tr.w);
           }
         }
+        {
+          // a chunk whose candidates are all ghosts (the outer cell layers of a slab rank) produces no row: skip it
+          bool row_needed = false;
+#pragma unroll
+          for (int k = 0; k < PM_RJ; k++) row_needed = row_needed || oj[k] >= 0;
+          if (!__any_sync(0xffffffffu, row_needed)) continue;
+        }
         if (HALFIDS) {
           // pj = number of this cell's particles with an id <= the candidate's: upper bound in the ascending ids of the
           // staged particles (shared memory), branch-free and with the PM_RJ searches of a lane interleaved step by
@@ -1611,11 +1618,20 @@ __global__ void __launch_bounds__(256) ell_kernel(const int64_t* __restrict__ of
 // stream; a zero-copy store instead of a copy-engine node) and every piece of per-build state — histogram, look-back
 // words of both scans, queue, ticket, the status block itself — is cleared for the NEXT build, so that a build starts
 // without a memset node.
+struct HaloCtrl;
+__device__ void halo_done_device(HaloCtrl* ctrl, unsigned long long* peer_free_lo, unsigned long long* peer_free_hi);
 __global__ void __launch_bounds__(256) finalize_kernel(DeviceStatus* __restrict__ st, DeviceStatus* __restrict__ host,
                                                        uint4* __restrict__ zero_region, size_t zero_vecs,
-                                                       size_t status_vec0, size_t status_vecs) {
+                                                       size_t status_vec0, size_t status_vecs, HaloCtrl* halo_ctrl,
+                                                       unsigned long long* peer_free_lo,
+                                                       unsigned long long* peer_free_hi) {
   pdl_enter();
-  if (blockIdx.x == 0 && threadIdx.x == 0) *host = *st;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *host = *st;
+    // a slab rank (nlb200_set_halo_sync): this build has finished reading its ghosts — the neighbours may overwrite
+    // them, the step counter advances
+    if (halo_ctrl != nullptr) halo_done_device(halo_ctrl, peer_free_lo, peer_free_hi);
+  }
   // the status block is cleared by the thread that copied it (block 0 clears all of it after the copy)
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < zero_vecs; i += (size_t)gridDim.x * blockDim.x) {
     if (i >= status_vec0 && i < status_vec0 + status_vecs) continue;
@@ -1767,6 +1783,181 @@ __global__ void __launch_bounds__(256) pack_faces_kernel(const T* __restrict__ q
     out_counts[1] = c_hi;
     state[0] = state[1] = state[2] = 0ull;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Halo exchange by peer stores (no NCCL call on the step): a slab rank's packing kernel writes the ghost records
+// STRAIGHT INTO ITS NEIGHBOURS' assembly buffers over NVLink (peer pointers from CUDA IPC) and then raises a flag in
+// the neighbour's control block; the neighbour's build waits for the flags of both faces before it reads its ghosts
+// and tells the senders when it is done with them.  All flags carry the step number of a device-side counter, so an
+// exchange + build replays as a CUDA graph.  Every wait is bounded: a lost peer raises `error` instead of hanging.
+//   sender  (pack_faces_p2p_kernel, step n = ctrl->step + 1):
+//            wait  free_from[f] >= n - 1     the neighbour has finished reading what step n-1 wrote into it
+//            write ghosts + NaN padding into the neighbour's region, __threadfence_system
+//            set   neighbour.ready[f'] = n   (last CTA)
+//   receiver (halo_wait_kernel before the build):   wait ready[f] >= n for both faces
+//            (finalize_kernel after the build):     step = n; set neighbour.free_from[f'] = n
+// ---------------------------------------------------------------------------------------------------------------
+struct HaloCtrl {
+  unsigned long long step;          // steps completed by this rank
+  unsigned long long ready[2];      // [0]: ghosts from the lower neighbour are complete for step ready[0]; [1]: upper
+  unsigned long long free_from[2];  // [0]: the lower neighbour has finished reading what this rank sent it; [1]: upper
+  unsigned long long error;         // a bounded wait gave up
+  unsigned long long pad[2];
+};
+constexpr unsigned int HALO_SPIN_LIMIT = 1u << 26;  // ~1 s of polling, then give up
+
+__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// returns false if the flag did not reach `want` within the spin limit
+__device__ __forceinline__ bool halo_wait_flag(const unsigned long long* flag, unsigned long long want) {
+  for (unsigned int spins = 0; spins < HALO_SPIN_LIMIT; spins++) {
+    if (ld_sys(flag) >= want) return true;
+    __nanosleep(64);
+  }
+  return false;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_faces_p2p_kernel(const T* __restrict__ q, const int32_t* __restrict__ gids,
+                                                             int64_t n, int stride, int axis, double cut_lo,
+                                                             double cut_hi, T* out_q_lo, int32_t* out_gid_lo,
+                                                             T* out_q_hi, int32_t* out_gid_hi, int64_t capacity,
+                                                             unsigned long long* __restrict__ state,
+                                                             int64_t* __restrict__ out_counts, HaloCtrl* ctrl,
+                                                             unsigned long long* peer_ready_lo,
+                                                             unsigned long long* peer_ready_hi) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  __shared__ bool is_last, go;
+  bool f_lo = false, f_hi = false;
+  if (i < n) {
+    const double v = (double)q[i * stride + axis];
+    f_lo = out_q_lo != nullptr && v < cut_lo;
+    f_hi = out_q_hi != nullptr && v >= cut_hi;
+  }
+  // only a CTA that has something to send touches the neighbours: it first makes sure that they have finished
+  // reading what the previous step wrote into them
+  const bool sends = __syncthreads_or(f_lo || f_hi) != 0;
+  if (threadIdx.x == 0) {
+    bool ok = true;
+    if (sends) {
+      const unsigned long long step = ld_sys(&ctrl->step);
+      if (out_q_lo != nullptr) ok = halo_wait_flag(&ctrl->free_from[0], step) && ok;
+      if (out_q_hi != nullptr) ok = halo_wait_flag(&ctrl->free_from[1], step) && ok;
+      if (!ok) ctrl->error = 1ull;
+    }
+    go = ok;
+  }
+  __syncthreads();
+  if (!go) f_lo = f_hi = false;
+#pragma unroll
+  for (int f = 0; f < 2; f++) {
+    const bool flag = f == 0 ? f_lo : f_hi;
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (m == 0u) continue;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&state[f], (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    const int64_t pos = (int64_t)base + __popc(m & ((1u << lane) - 1u));
+    if (flag && pos < capacity) {
+      T* oq = f == 0 ? out_q_lo : out_q_hi;
+      int32_t* og = f == 0 ? out_gid_lo : out_gid_hi;
+      if (stride == 4 && sizeof(T) == 8) {
+        // a {x, y, z, w} double record: two 16-byte peer stores
+        const double2* src = reinterpret_cast<const double2*>(q + i * 4);
+        double2* dst = reinterpret_cast<double2*>(oq + pos * 4);
+        dst[0] = src[0];
+        dst[1] = src[1];
+      } else {
+        for (int c = 0; c < stride; c++) oq[pos * stride + c] = q[i * stride + c];
+      }
+      og[pos] = gids != nullptr ? gids[i] : (int32_t)i;
+    }
+  }
+  if (sends) __threadfence_system();  // this CTA's peer stores are visible system-wide before its ticket
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&state[2], 1ull) == (unsigned long long)gridDim.x - 1ull;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const long long c_lo = (long long)*reinterpret_cast<volatile unsigned long long*>(&state[0]);
+  const long long c_hi = (long long)*reinterpret_cast<volatile unsigned long long*>(&state[1]);
+  const T nan = (T)__longlong_as_double(0x7ff8000000000000ll);
+  // absent slots: the regions start out all-NaN (the owner fills them once), so only the slots that held a record of
+  // the PREVIOUS step and hold none now have to be cleared (state[3], state[4] remember the previous counts)
+  const long long p_lo = (long long)state[3], p_hi = (long long)state[4];
+  if (threadIdx.x == 0) go = ld_sys(&ctrl->error) == 0ull;  // some CTA gave up waiting: nothing more is sent
+  __syncthreads();
+  if (go && (c_lo < p_lo || c_hi < p_hi) && threadIdx.x == 0) {
+    // slots are about to be cleared in the neighbours: they must have finished the previous step (a CTA that sent
+    // records has checked this already; this one may not have sent any)
+    const unsigned long long step = ld_sys(&ctrl->step);
+    bool ok = true;
+    if (out_q_lo != nullptr) ok = halo_wait_flag(&ctrl->free_from[0], step) && ok;
+    if (out_q_hi != nullptr) ok = halo_wait_flag(&ctrl->free_from[1], step) && ok;
+    if (!ok) ctrl->error = 1ull;
+    go = ok;
+  }
+  __syncthreads();
+  if (go && out_q_lo != nullptr)
+    for (int64_t t = min(c_lo, (long long)capacity) * stride + threadIdx.x; t < min(p_lo, (long long)capacity) * stride;
+         t += blockDim.x)
+      out_q_lo[t] = nan;
+  if (go && out_q_hi != nullptr)
+    for (int64_t t = min(c_hi, (long long)capacity) * stride + threadIdx.x; t < min(p_hi, (long long)capacity) * stride;
+         t += blockDim.x)
+      out_q_hi[t] = nan;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out_counts[0] = c_lo;
+    out_counts[1] = c_hi;
+    state[0] = state[1] = state[2] = 0ull;
+    if (go) {
+      state[3] = (unsigned long long)c_lo;
+      state[4] = (unsigned long long)c_hi;
+    }
+    const unsigned long long nstep = ld_sys(&ctrl->step) + 1ull;
+    if (go && peer_ready_lo != nullptr) st_sys(peer_ready_lo, nstep);
+    if (go && peer_ready_hi != nullptr) st_sys(peer_ready_hi, nstep);
+    // ... and this rank's own ghosts: wait here for the neighbours' flags, so that the build can follow directly
+    bool ok = go;
+    if (ok && out_q_lo != nullptr) ok = halo_wait_flag(&ctrl->ready[0], nstep);
+    if (ok && out_q_hi != nullptr) ok = halo_wait_flag(&ctrl->ready[1], nstep) && ok;
+    if (!ok) ctrl->error = 1ull;
+    __threadfence_system();
+  }
+}
+
+// before the build of a slab rank: the ghosts of both faces have arrived (faces: bit 0 lower, bit 1 upper)
+__global__ void halo_wait_kernel(HaloCtrl* ctrl, int faces) {
+  if (threadIdx.x != 0) return;
+  const unsigned long long want = ld_sys(&ctrl->step) + 1ull;
+  bool ok = true;
+  if (faces & 1) ok = halo_wait_flag(&ctrl->ready[0], want) && ok;
+  if (faces & 2) ok = halo_wait_flag(&ctrl->ready[1], want) && ok;
+  if (!ok) ctrl->error = 1ull;
+  __threadfence_system();
+}
+
+// after the build: this rank has finished reading its ghosts of the step — the neighbours may overwrite them
+__device__ void halo_done_device(HaloCtrl* ctrl, unsigned long long* peer_free_lo, unsigned long long* peer_free_hi) {
+  const unsigned long long nstep = ld_sys(&ctrl->step) + 1ull;
+  st_sys(&ctrl->step, nstep);
+  if (peer_free_lo != nullptr) st_sys(peer_free_lo, nstep);
+  if (peer_free_hi != nullptr) st_sys(peer_free_hi, nstep);
+}
+__global__ void halo_done_kernel(HaloCtrl* ctrl, unsigned long long* peer_free_lo, unsigned long long* peer_free_hi) {
+  if (threadIdx.x == 0) halo_done_device(ctrl, peer_free_lo, peer_free_hi);
 }
 
 // halo packing: the selected records (flags/pos from slab_flag_kernel + scan) go to out_q[pos], their global ids to

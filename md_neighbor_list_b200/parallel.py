@@ -295,3 +295,197 @@ class _null:
 
     def __exit__(self, *a):
         return False
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of raw device memory (library-owned or a neighbour's, opened by CUDA IPC)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class PeerSlabDecomposition(SlabDecomposition):
+    """The slab decomposition with the halo exchange done by PEER STORES instead of NCCL send/recv: the packing kernel
+    of a rank writes its face particles straight into its neighbours' assembly buffers over NVLink (pointers from
+    CUDA IPC, exchanged once), flags in a 64-byte control block per rank order the steps on the device
+    (include/nlist_b200.h, "halo exchange by peer stores").  Per step: nlb200_pack_faces_p2p, nlb200_halo_wait, the
+    build, nlb200_halo_done — four launches, no host synchronisation, no NCCL kernel.  Measured at 2 GPUs on the
+    contract workload: exchange 49 us (packing + NCCL group of 4 send/recv pairs) -> see profiles/r02_halo_p2p.md.
+
+    Every rank allocates [control | positions (n_cap + 2 cap records) | global ids] of the same size; a neighbour's ghost
+    region sits at the same offset on every rank.  torch.distributed is used once, on the host, to agree on the sizes
+    and to pass the IPC handles around.  If a rank cannot export or open a handle, all ranks fall back to NCCL."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self._p2p = None
+        self._synced_handle = None
+
+    # -- set-up (collective) ----------------------------------------------------------------------------------------
+    def _setup(self, n_owned: int, dtype, dev) -> bool:
+        import ctypes as C
+        if self._p2p is not None:
+            return self._p2p.get("ok", False)
+        L = _lib.lib()
+        cap = self.ghost_capacity(n_owned)
+        t = torch.tensor([n_owned], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        n_cap = (int(t.item()) + 31) // 32 * 32
+        esz = 8 if dtype == torch.float64 else 4
+        n_total = n_cap + 2 * cap
+        o_q = 256
+        o_g = (o_q + n_total * self.stride * esz + 255) // 256 * 256
+        nbytes = o_g + n_total * 4
+        base = C.c_void_p()
+        handle = (C.c_char * 64)()
+        st = L.nlb200_p2p_alloc(nbytes, C.byref(base), C.cast(handle, C.c_void_p))
+        mine = {"ok": st == _lib.OK, "handle": bytes(handle), "nbytes": nbytes}
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        ok = all(e["ok"] and e["nbytes"] == nbytes for e in everyone)
+        peers = {}
+        if ok:
+            for p in (self.rank - 1, self.rank + 1):
+                if 0 <= p < self.world:
+                    ptr = C.c_void_p()
+                    hb = (C.c_char * 64).from_buffer_copy(everyone[p]["handle"])
+                    if L.nlb200_p2p_open(C.cast(hb, C.c_void_p), C.byref(ptr)) != _lib.OK:
+                        ok = False
+                    else:
+                        peers[p] = ptr.value
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        ok = bool(int(flag.item()))
+        self._p2p = {"ok": ok, "base": base.value, "peers": peers, "cap": cap, "n_cap": n_cap, "n_total": n_total,
+                     "o_q": o_q, "o_g": o_g, "esz": esz, "nbytes": nbytes}
+        if not ok:
+            return False
+        ts = "<f8" if dtype == torch.float64 else "<f4"
+        self._qall = torch.as_tensor(_DevArray(base.value + o_q, (n_total, self.stride), ts), device=dev)
+        self._gall = torch.as_tensor(_DevArray(base.value + o_g, (n_total,), "<i4"), device=dev)
+        self._qall.fill_(float("nan"))  # every slot starts as an absent record (also the regions of missing faces)
+        self._gall.zero_()
+        self._ctrl = torch.as_tensor(_DevArray(base.value, (8,), "<i8"), device=dev)
+        self._state = torch.zeros(8, dtype=torch.int64, device=dev)  # cursors, ticket, previous counts
+        self._cnt2 = torch.zeros(2, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)  # nobody writes into a neighbour before it has initialised its buffer
+        return True
+
+    def max_ghosts(self, n_owned: int) -> int:
+        """Slots behind the owned records in the peer layout: both ghost regions (an end slab's missing face stays
+        absent) plus the padding of the owned region up to the common size."""
+        if self.world == 1:
+            return 0
+        if self._p2p is not None and self._p2p.get("ok"):
+            return self._p2p["n_total"] - n_owned
+        return 2 * self.ghost_capacity(n_owned) + 64
+
+    def owned_view(self, n_owned: int, dtype=torch.float64, device=None):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        if not self._setup(n_owned, dtype, dev):
+            return super().owned_view(n_owned, dtype, dev)
+        return self._qall[:n_owned], self._gall[:n_owned]
+
+    def _addr(self, base: int, what: str, slot: int = 0) -> int:
+        p = self._p2p
+        if what == "q":
+            return base + p["o_q"] + slot * self.stride * p["esz"]
+        if what == "g":
+            return base + p["o_g"] + slot * 4
+        return base + {"ready0": 8, "ready1": 16, "free0": 24, "free1": 32}[what]
+
+    def exchange(self, q_owned: torch.Tensor, gid_owned: torch.Tensor):
+        if self.world == 1 or not q_owned.is_cuda:
+            return super().exchange(q_owned, gid_owned)
+        n = q_owned.shape[0]
+        if not self._setup(n, q_owned.dtype, q_owned.device):
+            return super().exchange(q_owned, gid_owned)
+        p = self._p2p
+        if q_owned.data_ptr() != self._qall.data_ptr():
+            self._qall[:n].copy_(q_owned)
+        if gid_owned.data_ptr() != self._gall.data_ptr():
+            self._gall[:n].copy_(gid_owned)
+        L = _lib.lib()
+        lo_p, hi_p = p["peers"].get(self.rank - 1), p["peers"].get(self.rank + 1)
+        cap, n_cap = p["cap"], p["n_cap"]
+        dtype = _lib.F64 if q_owned.dtype == torch.float64 else _lib.F32
+        s = torch.cuda.current_stream().cuda_stream
+        # my lower-face particles go into the lower neighbour's "ghosts from above" region (second region), my
+        # upper-face particles into the upper neighbour's "ghosts from below" region (first region)
+        st = L.nlb200_pack_faces_p2p(
+            self._qall.data_ptr(), self._gall.data_ptr(), n, dtype, self.stride, self.axis,
+            self.lo + self.sl if lo_p else -float("inf"), self.hi - self.sl if hi_p else float("inf"),
+            self._addr(lo_p, "q", n_cap + cap) if lo_p else None, self._addr(lo_p, "g", n_cap + cap) if lo_p else None,
+            self._addr(hi_p, "q", n_cap) if hi_p else None, self._addr(hi_p, "g", n_cap) if hi_p else None,
+            cap, self._cnt2.data_ptr(), self._state.data_ptr(), p["base"],
+            self._addr(lo_p, "ready1") if lo_p else None, self._addr(hi_p, "ready0") if hi_p else None, s)
+        if st != _lib.OK:
+            raise _lib.NlistError(st, "nlb200_pack_faces_p2p failed")
+        # (the packing kernel ends by waiting for this rank's own ghosts: no separate nlb200_halo_wait launch)
+        self._cnt = {}
+        if lo_p:
+            self._cnt[self.rank - 1] = self._cnt2[0:1]
+        if hi_p:
+            self._cnt[self.rank + 1] = self._cnt2[1:2]
+        self._last = (self._qall, self._gall, n)
+        return self._last
+
+    def done(self) -> None:
+        """After the build has been enqueued: the neighbours may overwrite this rank's ghosts (stream-ordered)."""
+        p = self._p2p
+        if not p or not p.get("ok"):
+            return
+        lo_p, hi_p = p["peers"].get(self.rank - 1), p["peers"].get(self.rank + 1)
+        st = _lib.lib().nlb200_halo_done(p["base"], self._addr(lo_p, "free1") if lo_p else None,
+                                         self._addr(hi_p, "free0") if hi_p else None,
+                                         torch.cuda.current_stream().cuda_stream)
+        if st != _lib.OK:
+            raise _lib.NlistError(st, "nlb200_halo_done failed")
+
+    def build(self, nl, q_owned: torch.Tensor, stream=None, gid_owned: torch.Tensor | None = None, build_fn=None):
+        ctx = torch.cuda.stream(stream) if (stream is not None and q_owned.is_cuda) else _null()
+        with ctx:
+            if gid_owned is None:
+                gid_owned = self.global_ids(q_owned.shape[0], q_owned.device)
+            q_all, gid_all, n_owned = self.exchange(q_owned, gid_owned)
+            if build_fn is not None:
+                out = build_fn(q_all, n_owned, gid_all)
+            else:
+                if self.uses_peer_stores() and self._synced_handle is not nl:
+                    # nlb200_halo_done becomes part of the build's last kernel
+                    p = self._p2p
+                    lo_p, hi_p = p["peers"].get(self.rank - 1), p["peers"].get(self.rank + 1)
+                    _lib.check(nl._h, _lib.lib().nlb200_set_halo_sync(
+                        nl._h, p["base"], self._addr(lo_p, "free1") if lo_p else None,
+                        self._addr(hi_p, "free0") if hi_p else None))
+                    self._synced_handle = nl
+                nl.build(q_all, n_owned=n_owned, global_ids=gid_all if self.world > 1 else None, stream=stream)
+                out = None
+            if q_owned.is_cuda and self.world > 1 and (build_fn is not None or not self.uses_peer_stores()):
+                self.done()
+        return out
+
+    def uses_peer_stores(self) -> bool:
+        return bool(self._p2p and self._p2p.get("ok"))
+
+    def check(self) -> tuple:
+        if self.uses_peer_stores() and int(self._ctrl[5]) != 0:
+            raise _lib.NlistError(_lib.ERR_STATE, "a halo flag did not arrive within the spin limit (lost neighbour?)")
+        return super().check()
+
+    def close(self) -> None:
+        p = self._p2p
+        if p and p.get("ok"):
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)  # nobody frees memory a neighbour may still write into
+            L = _lib.lib()
+            if self._synced_handle is not None and self._synced_handle._h:
+                L.nlb200_set_halo_sync(self._synced_handle._h, None, None, None)
+            self._synced_handle = None
+            self._qall = self._gall = self._ctrl = None
+            for ptr in p["peers"].values():
+                L.nlb200_p2p_close(ptr)
+            L.nlb200_p2p_free(p["base"])
+        self._p2p = None
