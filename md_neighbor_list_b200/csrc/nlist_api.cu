@@ -352,7 +352,14 @@ int pick_path(const nlb200_context* h, int64_t max_in_cell) {
   if (h->exact_only != 0 || h->variant == 1) return PATH_V1;
   if (h->variant == 5 || h->variant == 6 || (h->variant >= 20 && h->variant < 40)) return PATH_ROWMASK;
   if (h->variant != 0) return PATH_PAIRMASK;
-  return max_in_cell > PAIRMASK_MAX_CELL ? PATH_ROWMASK : PATH_PAIRMASK;
+  if (max_in_cell > PAIRMASK_MAX_CELL) return PATH_ROWMASK;
+  // Large systems: once the pair masks (324 bytes per particle at 3 words per stencil cell) no longer fit the L2 they
+  // make a round trip through HBM; the row masks hold one bit per evaluated test (~120 bytes per particle) and need no
+  // popcount pass over them.  Same build time within 1-2 % at 2 M and 16.8 M uniform particles
+  // (profiles/r02_large_systems.md), 40 % less mask traffic.
+  const int64_t wi = (std::max<int64_t>(max_in_cell, 1) + 31) / 32;
+  if (h->l2_bytes > 0 && 108 * wi * h->max_n > h->l2_bytes) return PATH_ROWMASK;
+  return PATH_PAIRMASK;
 }
 bool uses_v1(const nlb200_context* h) { return h->path == PATH_V1; }
 bool uses_rowmask(const nlb200_context* h) { return h->path == PATH_ROWMASK; }

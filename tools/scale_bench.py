@@ -53,7 +53,7 @@ else:
     gid_dev.copy_(torch.arange(n, dtype=torch.int32, device=dev) + rank * n)
 del q
 n_total = n + (halo.max_ghosts(n) if halo else 0)
-nl = VerletListB200(SL, *box, dtype="f64", mode=args.mode)
+nl = VerletListB200(SL, *box, dtype="f64", mode=args.mode, kernel_variant=int(os.environ.get("NLB_VARIANT", "0")))
 per_row = 4.18879 * SL ** 3 * DENS * (0.5 if args.mode == "half_csr" else 1.0)
 nl.initialize(n_total, int(n * per_row * 1.05) + 1024)
 stream = torch.cuda.Stream()
