@@ -692,6 +692,8 @@ def run_ours(args):
         #                    it is bounded by FP32 issue (3 FFMA + 1 FADD per distance test), reported beside it
         kern = {"emit": ("emit_kernel", 4 * entries_local + 12 * n),
                 "emit3": ("emit3_kernel", 4 * entries_local + 12 * n),
+                "emit_run": ("emitrun_kernel", 4 * entries_local + 12 * n),
+                "runmask": ("runmask_kernel", 16 * n),
                 "pairmask": ("pairmask_kernel", 16 * n),
                 "rowmask": ("rowmask4_kernel", 16 * n),
                 "search_fill": ("search_kernel<FILL>", n * (16 + 8) + 4 * entries_local),
@@ -713,7 +715,7 @@ def run_ours(args):
         if dom and os.path.exists(traffic_file):
             with open(traffic_file) as f:
                 roof["traffic"] = json.load(f).get(kern[dom][0])
-        search = "pairmask" if "pairmask" in stage_ms else ("rowmask" if "rowmask" in stage_ms else None)
+        search = next((k for k in ("runmask", "pairmask", "rowmask") if k in stage_ms), None)
         if search:
             # secondary ceiling: the distance tests themselves, 4 FP32-pipe lane-ops each at the measured
             # lane-FMA rate (profiles/r01_microbench_issue_rates.txt) x SM count x SM clock of this device
@@ -735,9 +737,9 @@ def run_ours(args):
                              f"(the reference is single-threaded); ms/build: "
                              + ", ".join(f"{k}={v:.1f}" for k, v in times.items()),
                    "ms_per_build": times, "host_nproc": os.cpu_count()}
-        # kernels of one build: bin (+ cell scan), scatter, cellsort, pairmask, rowcount, scan(counts), emit, finalize
+        # kernels of one build: bin (+ cell scan), scatter, cellsort, runmask, scan(counts), emitrun, finalize
         # (+ the halo packing of a slab rank: one kernel)
-        kernels_per_build = 8 if world == 1 else 8 + 1
+        kernels_per_build = 7 if world == 1 else 7 + 1
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

@@ -16,6 +16,7 @@
 #include "../../include/nlist_b200.h"
 #include "nlist_kernels.cuh"
 #include "nlist_rowmask.cuh"
+#include "nlist_runmask.cuh"
 
 #ifndef NLB_RM4_RJ
 #define NLB_RM4_RJ 8  // candidates per lane of the row-mask search (packed in pairs)
@@ -67,6 +68,7 @@ struct nlb200_context {
   uint32_t* mask = nullptr;  // [27][mask_wi][mask_ncap] pair-mask words
   int32_t mask_wi = 0;       // words per (row, stencil cell): cells may hold up to 32*mask_wi particles
   int64_t mask_ncap = 0;
+  int32_t mask_wr = 0;       // run-mask path: words per (row, run); the buffer is [9][mask_wr][mask_ncap]
   CellRec* cellrec = nullptr;    // [M] per-cell records of the row-mask path
   uint32_t* rmask = nullptr;     // row-mask words (per-cell blocks handed out by a cursor)
   int64_t rmask_cap = 0;         // ... capacity in words
@@ -114,10 +116,12 @@ struct nlb200_context {
 };
 
 enum StageId { ST_ZERO = 0, ST_BIN, ST_SCAN_CELLS, ST_SCATTER, ST_CELLSORT, ST_COUNT, ST_SCAN_COUNTS, ST_FILL,
-               ST_SORT_ROWS, ST_ELL, ST_STATUS, ST_PAIRMASK, ST_ROWCOUNT, ST_EMIT, ST_ROWMASK, ST_EMIT3, ST_NUM };
+               ST_SORT_ROWS, ST_ELL, ST_STATUS, ST_PAIRMASK, ST_ROWCOUNT, ST_EMIT, ST_ROWMASK, ST_EMIT3, ST_RUNMASK,
+               ST_EMITRUN, ST_NUM };
 static const char* const kStageNames[ST_NUM] = {"zero", "bin", "scan_cells", "scatter", "cellsort", "search_count",
                                                 "scan_counts", "search_fill", "sort_rows", "ell", "status_copy",
-                                                "pairmask", "row_count", "emit", "rowmask", "emit3"};
+                                                "pairmask", "row_count", "emit", "rowmask", "emit3", "runmask",
+                                                "emit_run"};
 
 namespace {
 
@@ -302,6 +306,15 @@ cudaError_t set_pm_attr() {
                               MAX_EMIT_SMEM);
 }
 
+cudaError_t set_runmask_attrs() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(runmask_kernel<double, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(runmask_kernel<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(runmask_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(runmask_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(emitrun_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM);
+}
+
 cudaError_t set_search_attrs() {
   cudaError_t e;
   if ((e = set_pm_attr<double, 4>()) != cudaSuccess) return e;
@@ -346,13 +359,16 @@ cudaError_t launch_search(bool half, bool fill, bool exact, const SearchArgs<T>&
 //   1, or NLB200_OPT_EXACT_ONLY: search_kernel twice (count, fill): every test in the input precision if asked
 //   2, 3, 4, 7, 100..:           pair masks and their ablations
 //   5: row masks with the CTA-per-cell search (rowmask_kernel)      6, 20..39: row masks (rowmask4_kernel)
-enum { PATH_V1 = 1, PATH_PAIRMASK = 2, PATH_ROWMASK = 3 };
+//   8, or the default for FULL lists: RUN MASKS (runmask_kernel, emitrun_kernel; nlist_runmask.cuh)
+enum { PATH_V1 = 1, PATH_PAIRMASK = 2, PATH_ROWMASK = 3, PATH_RUNMASK = 4 };
 constexpr int64_t PAIRMASK_MAX_CELL = 256;
 int pick_path(const nlb200_context* h, int64_t max_in_cell) {
   if (h->exact_only != 0 || h->variant == 1) return PATH_V1;
   if (h->variant == 5 || h->variant == 6 || (h->variant >= 20 && h->variant < 40)) return PATH_ROWMASK;
-  if (h->variant != 0) return PATH_PAIRMASK;
+  if (h->variant != 0 && h->variant != 8) return PATH_PAIRMASK;
   if (max_in_cell > PAIRMASK_MAX_CELL) return PATH_ROWMASK;
+  if (h->mode != NLB200_HALF_CSR) return PATH_RUNMASK;  // 36 bytes x words-per-run per particle, dense
+  if (h->variant == 8) return PATH_PAIRMASK;
   // Large systems: once the pair masks (324 bytes per particle at 3 words per stencil cell) no longer fit the L2 they
   // make a round trip through HBM; the row masks hold one bit per evaluated test (~120 bytes per particle) and need no
   // popcount pass over them.  Same build time within 1-2 % at 2 M and 16.8 M uniform particles
@@ -363,6 +379,7 @@ int pick_path(const nlb200_context* h, int64_t max_in_cell) {
 }
 bool uses_v1(const nlb200_context* h) { return h->path == PATH_V1; }
 bool uses_rowmask(const nlb200_context* h) { return h->path == PATH_ROWMASK; }
+bool uses_runmask(const nlb200_context* h) { return h->path == PATH_RUNMASK; }
 
 template <typename T, int STRIDE, int HALFMODE>
 cudaError_t set_rm_attr_h() {
@@ -519,7 +536,8 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     else
       CK(h, launch_chain(cellsort_kernel<T, STRIDE, false>, dim3((unsigned)cs_blocks), dim3(128), 0, s, q, gp,
                          (const int32_t*)h->cell_start, (const int32_t*)h->perm, h->sorted_ids, h->rec, h->slot_cell,
-                         gids, h->slot_gid, (CellRec*)nullptr, 0ull, (int32_t*)nullptr, 0, h->status_dev, 1));
+                         gids, h->slot_gid, (CellRec*)nullptr, 0ull, uses_runmask(h) ? h->counts : (int32_t*)nullptr,
+                         (int32_t)n_owned, h->status_dev, 1));
   }
   const bool half = h->mode == NLB200_HALF_CSR;
   const bool use_v1 = uses_v1(h);
@@ -600,6 +618,80 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
       em.st = h->status_dev;
       constexpr int rows = EM3_WARPS * 32;
       CK(h, launch_chain(emit3_kernel, dim3((unsigned)((n + rows - 1) / rows)), dim3(rows),
+                         (size_t)rows * EM_LINE * sizeof(int32_t), s, em));
+    }
+  } else if (uses_runmask(h)) {
+    // --- FULL lists: run masks.  Search (every ordered pair once; bits = the particles of an x-run, row lengths
+    //     by RED) -> offsets -> emission. ---
+    CK(h, stage(ST_RUNMASK));
+    if (n > 0) {
+      RunMaskArgs<T> rn;
+      rn.q = q;
+      rn.gp = gp;
+      rn.cell_start = h->cell_start;
+      rn.rec = h->rec;
+      rn.sorted_ids = h->sorted_ids;
+      rn.n_owned = (int32_t)n_owned;
+      rn.mask = h->mask;
+      rn.n_cap = h->mask_ncap;
+      rn.wr = h->mask_wr;
+      rn.fits32 = (9ll * h->mask_wr * h->mask_ncap) < (1ll << 32) ? 1 : 0;
+      rn.band = gp.band * 1.25f;  // rows reach 1.5 cells from the centre in x here
+      rn.queue = h->queue;
+      rn.counts = h->counts;
+      rn.st = h->status_dev;
+      const size_t rn_smem = rn_warp_bytes(h->mask_wr) * (RN_THREADS / 32);
+      int per_sm = 0;
+      CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, runmask_kernel<T, STRIDE>, RN_THREADS, rn_smem));
+      if (per_sm < 1) return fail(h, NLB200_ERR_CUDA, "run-mask kernel does not fit an SM (%zu bytes of shared memory)", rn_smem);
+      int64_t grid = (int64_t)per_sm * h->sm_count;
+      const int64_t resident = grid * (RN_THREADS / 32);
+      // units per cell: one chunk of RN_CH candidates each for a mean column (9 cells); longer columns loop
+      int64_t parts = (int64_t)(9.0 * ((double)n / (double)M) * 1.1 / (double)RN_CH + 0.999);
+      if (parts < 1) parts = 1;
+      if (parts > 16) parts = 16;
+      if (h->variant >= 100 && h->variant < 200) parts = h->variant - 100;  // tuning override
+      rn.parts = (int32_t)parts;
+      int64_t grab = (M * parts) / (resident * 64);
+      if (grab < 1) grab = 1;
+      if (grab > 64) grab = 64;
+      rn.grab = (int32_t)grab;
+      if (M * parts >= (1ll << 31)) return fail(h, NLB200_ERR_INVALID, "cells x parts exceeds 2^31 units");
+      rn.d_parts = make_fastdiv((uint32_t)parts);
+      rn.d_mx = make_fastdiv((uint32_t)gp.mesh[0]);
+      rn.d_my = make_fastdiv((uint32_t)gp.mesh[1]);
+      const int64_t need = (M * parts + RN_THREADS / 32 - 1) / (RN_THREADS / 32);
+      if (grid > need) grid = need;
+      CK(h, launch_chain(runmask_kernel<T, STRIDE>, dim3((unsigned)grid), dim3(RN_THREADS), rn_smem, s, rn));
+    }
+    CK(h, stage(ST_SCAN_COUNTS));
+    {
+      const int tiles = (int)((n_owned + SCAN_TILE - 1) / SCAN_TILE);
+      CK(h, launch_chain(scan_kernel<int64_t>, dim3(tiles > 0 ? tiles : 1), dim3(SCAN_THREADS), 0, s,
+                         (const int32_t*)h->counts, (int64_t)n_owned, h->offsets, h->offsets32, h->scan_state_counts,
+                         h->status_dev, &h->status_dev->max_partners, (long long)h->cap_entries));
+    }
+    CK(h, stage(ST_EMITRUN));
+    if (n > 0) {
+      EmitRunArgs em;
+      em.cell_start = h->cell_start;
+      em.sorted_ids = h->sorted_ids;
+      em.slot_cell = h->slot_cell;
+      em.slot_pid = gids != nullptr ? h->slot_gid : h->sorted_ids;
+      for (int d = 0; d < 3; d++) em.mesh[d] = gp.mesh[d];
+      em.d_mx = make_fastdiv((uint32_t)gp.mesh[0]);
+      em.d_my = make_fastdiv((uint32_t)gp.mesh[1]);
+      em.n_total = n;
+      em.n_owned = (int32_t)n_owned;
+      em.n_cells = M;
+      em.mask = h->mask;
+      em.n_cap = h->mask_ncap;
+      em.wr = h->mask_wr;
+      em.offsets = h->offsets;
+      em.partners = h->partners;
+      em.capacity = h->cap_entries;
+      constexpr int rows = ER_WARPS * 32;
+      CK(h, launch_chain(emitrun_kernel, dim3((unsigned)((n + rows - 1) / rows)), dim3(rows),
                          (size_t)rows * EM_LINE * sizeof(int32_t), s, em));
     }
   } else if (use_v1) {
@@ -813,6 +905,30 @@ cudaError_t settle_before_realloc(nlb200_context* h) {
   return cudaSuccess;
 }
 
+// Run masks: [9][wr][ncap] words, wr = words per (row, run).  A run is up to 3 cells: 3 * max_in_cell bounds it.
+int alloc_runmask(nlb200_context* h, int64_t max_in_run) {
+  int64_t wr = (max_in_run + 31) / 32;
+  if (wr < 1) wr = 1;
+  const int64_t ncap = (int64_t)align_up((size_t)(h->max_n > 0 ? h->max_n : 1), 32);
+  if (h->mask && h->mask_wr == wr && h->mask_ncap == ncap) return NLB200_OK;
+  uint32_t* fresh = nullptr;
+  CK(h, cudaMalloc(&fresh, sizeof(uint32_t) * (size_t)(9 * wr * ncap)));
+  if (h->mask) cudaFree(h->mask);
+  h->mask = fresh;
+  h->mask_wr = (int32_t)wr;
+  h->mask_wi = 0;
+  h->mask_ncap = ncap;
+  return NLB200_OK;
+}
+
+int64_t estimate_max_in_run(const nlb200_context* h, int64_t n) {
+  // mean occupancy of three cells + 6 sigma (Poisson) + slack; at least 192 (6 words): a slab rank without a cell
+  // window bins on the global grid, so n / cells underestimates its density
+  const double avg3 = 3.0 * (double)n / (double)h->n_cells;
+  const int64_t est = (int64_t)(avg3 + 6.0 * std::sqrt(avg3) + 8.0);
+  return est < 192 ? 192 : est;
+}
+
 int alloc_rmask(nlb200_context* h, int64_t words) {
   uint32_t* fresh = nullptr;
   CK(h, cudaMalloc(&fresh, sizeof(uint32_t) * (size_t)(words > 0 ? words : 1)));
@@ -823,7 +939,8 @@ int alloc_rmask(nlb200_context* h, int64_t words) {
 }
 
 // Buffers of the handle's search path for cells of up to `mic` particles.
-int alloc_search_buffers(nlb200_context* h, int64_t mic) {
+// mic_is_bound: mic was given by the caller or seen in a build (else it is initialize's density estimate).
+int alloc_search_buffers(nlb200_context* h, int64_t mic, bool mic_is_bound = false) {
   const int64_t n = h->max_n > 0 ? h->max_n : 1;
   const int64_t M = h->n_cells;
   if (uses_rowmask(h)) {
@@ -859,8 +976,12 @@ int alloc_search_buffers(nlb200_context* h, int64_t mic) {
       cudaFree(h->mask);
       h->mask = nullptr;
       h->mask_wi = 0;
+      h->mask_wr = 0;
     }
     return NLB200_OK;
+  }
+  if (uses_runmask(h)) {
+    return alloc_runmask(h, mic_is_bound ? 3 * mic : estimate_max_in_run(h, n));
   }
   if (!uses_v1(h)) return alloc_mask(h, mic);
   return NLB200_OK;
@@ -993,6 +1114,7 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
   CK(h, set_search_attrs());
   CK(h, set_rowmask_attrs());
   CK(h, set_rowmask4_attrs());
+  CK(h, set_runmask_attrs());
   free_buffers(h);
   const int64_t n = max_particles > 0 ? max_particles : 1;
   const int64_t M = h->n_cells;
@@ -1048,7 +1170,7 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
   {
     const int64_t mic = h->max_in_cell_opt > 0 ? h->max_in_cell_opt : estimate_max_in_cell(h, n);
     h->path = pick_path(h, mic);
-    rc = alloc_search_buffers(h, mic);
+    rc = alloc_search_buffers(h, mic, h->max_in_cell_opt > 0);
     if (rc) return rc;
   }
   if (h->mode == NLB200_FULL_ELL_TRANSPOSED) {
@@ -1088,15 +1210,17 @@ int nlb200_reserve_cell_capacity(nlb200_handle h, int64_t max_in_cell) {
     CK(h, settle_before_realloc(h));
     return alloc_rmask(h, need);
   }
-  if (max_in_cell <= (int64_t)h->mask_wi * 32) return NLB200_OK;
+  if (uses_runmask(h) ? 3 * max_in_cell <= (int64_t)h->mask_wr * 32 : max_in_cell <= (int64_t)h->mask_wi * 32)
+    return NLB200_OK;
   CK(h, settle_before_realloc(h));
   if (pick_path(h, max_in_cell) == PATH_ROWMASK) {
     // crowded cells: the per-particle planes of the pair masks would grow with the most crowded cell; the row masks
     // grow with the number of tests.  The first build on the new path reports how many words it needs.
     h->path = PATH_ROWMASK;
     h->rmask_need = 0;
-    return alloc_search_buffers(h, max_in_cell);
+    return alloc_search_buffers(h, max_in_cell, true);
   }
+  if (uses_runmask(h)) return alloc_runmask(h, 3 * max_in_cell);
   return alloc_mask(h, max_in_cell);
 }
 
@@ -1226,8 +1350,11 @@ int nlb200_synchronize(nlb200_handle h) {
     return fail(h, NLB200_ERR_CELL_CAPACITY, "the row masks need %lld words, the buffer holds %lld (most crowded cell: %d)",
                 (long long)st.mask_words, (long long)h->rmask_cap, st.max_in_cell);
   if (st.flags & FLAG_CELL_WORDS)
-    return fail(h, NLB200_ERR_CELL_CAPACITY, "a cell holds %d particles, the pair-mask words cover %d", st.max_in_cell,
-                h->mask_wi * 32);
+    return uses_runmask(h)
+               ? fail(h, NLB200_ERR_CELL_CAPACITY, "a run of three cells holds more than the %d particles the run-mask words cover (most crowded cell: %d)",
+                      h->mask_wr * 32, st.max_in_cell)
+               : fail(h, NLB200_ERR_CELL_CAPACITY, "a cell holds %d particles, the pair-mask words cover %d", st.max_in_cell,
+                      h->mask_wi * 32);
   if (st.flags & FLAG_CAPACITY)
     return fail(h, NLB200_ERR_CAPACITY, "partner list needs %lld entries, capacity is %lld",
                 (long long)st.total_entries, (long long)h->cap_entries);

@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, 
       // the id a row reports for this particle: with a local -> global map (multi-GPU) the emission gathers the
       // global id straight from the slot instead of slot -> local id -> global id
       if (global_ids != nullptr) slot_pid[beg + rank] = key;
-      if (cellrec != nullptr && id < n_owned) counts[id] = 0;
+      if (counts != nullptr && id < n_owned) counts[id] = 0;
     }
   }
   if (cellrec != nullptr) {
