@@ -390,7 +390,7 @@ constexpr int ER_WARPS = NLB_ER_WARPS;
 #define NLB_ER_MINB 14
 #endif
 #ifndef NLB_ER_VEC
-#define NLB_ER_VEC 4
+#define NLB_ER_VEC 8
 #endif
 constexpr int ER_VEC = NLB_ER_VEC;  // entries per vector store of the flush: 4 (16 bytes) or 8 (32 bytes)
 constexpr int ER_PRE = 4;  // words of a run requested ahead (runs of up to 128 particles)
@@ -510,8 +510,15 @@ __global__ void __launch_bounds__(ER_WARPS * 32, NLB_ER_MINB) emitrun_kernel(Emi
         if (u < nwmax) expand(m[u], s0 + 32 * u + 31);
     } else {
       // a long run (the row's own run can hold more partners than a line, crowded cells more than ER_PRE words):
-      // word by word with a check before each
-      for (int32_t w = 0; w < nwmax; w++) {
+      // word by word with a check before each — the requested words from their registers, the rest on demand
+#pragma unroll
+      for (int u = 0; u < ER_PRE; u++) {
+        if (u < nwmax && __any_sync(0xffffffffu, m[u] != 0u)) {
+          if (__any_sync(0xffffffffu, fill + __popc(m[u]) > EM_TILE)) flush(false);
+          expand(m[u], s0 + 32 * u + 31);
+        }
+      }
+      for (int32_t w = ER_PRE; w < nwmax; w++) {
         const uint32_t word = w < nw ? __ldg(mrow + ((long long)(r * a.wr + w)) * a.n_cap) : 0u;
         if (!__any_sync(0xffffffffu, word != 0u)) continue;
         if (__any_sync(0xffffffffu, fill + __popc(word) > EM_TILE)) flush(false);

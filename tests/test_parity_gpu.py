@@ -692,7 +692,8 @@ def test_kernel_variants_emit_identical_lists(cuda, oracle, mode):
     box = (23.0, 23.0, 23.0)
     # 4 = HALF rows filtered by id during the emission (the multi-GPU path) instead of inside the masks
     # 7 = mask indices in 64-bit arithmetic (the path of systems whose masks exceed 2^32 words)
-    outs = [gpu_build(cuda, q, 3.3, box, mode, kernel_variant=v) for v in (1, 2, 3, 4, 7, 5, 6, 0)]
+    # 8 = run masks (the default of FULL lists; HALF lists fall back to the pair masks)
+    outs = [gpu_build(cuda, q, 3.3, box, mode, kernel_variant=v) for v in (1, 2, 3, 4, 7, 5, 6, 8, 0)]
     for o in outs[1:]:
         assert o["pairs"] == outs[0]["pairs"]
         assert np.array_equal(o["np"], outs[0]["np"])
@@ -765,6 +766,93 @@ def test_row_mask_path_on_every_input_class(cuda, oracle, variant):
             g = perm[li]
             assert np.array_equal(lst[off[li]:off[li + 1]], ref.partners[ref.offsets[g]:ref.offsets[g + 1]])
         nl.close()
+
+
+def test_run_mask_path_on_every_input_class(cuda, oracle):
+    """The run-mask search + emission (FULL lists' default: rows of an x-run as bits, the column's particles on the
+    lanes; nlist_runmask.cuh) on the inputs that exercise its special cases: 3-cell axes (runs and columns cover the
+    whole axis), empty cells and runs, runs of more words than the emission requests ahead (> 128 particles) and of
+    more than one staged row round (> 256), the words-per-run capacity grown after a failed build, FP32 positions,
+    pairs on the search radius, duplicates, owned subsets with a global-id map, stencil order of the rows."""
+    from md_neighbor_list_b200 import NlistError, VerletListB200, _lib, workloads
+    torch = cuda
+    rng = np.random.default_rng(11)
+    box = (13.0, 29.5, 10.1)
+    q = np.zeros((5000, 4))
+    q[:, :3] = rng.random((5000, 3)) * np.array(box)
+    q[150:170, :3] = q[170:190, :3]  # duplicates: r2 == 0 (only the row's own bit is dropped)
+    got = gpu_build(cuda, q, 3.3, box, "full_csr")
+    assert_matches(oracle, got, oracle.bruteforce(q, 3.3, full=True))
+    ref = oracle.build_full(q, 3.3, box)
+    assert np.array_equal(got["list"], ref.partners)  # rows in stencil order: the reference kernels' discovery order
+    q = np.zeros((300, 4))
+    q[:, :3] = rng.random((300, 3)) * 60.0
+    got = gpu_build(cuda, q, 3.3, (60.0,) * 3, "full_csr")
+    assert_matches(oracle, got, oracle.bruteforce(q, 3.3, full=True))
+    # ~100 particles per cell: runs of ~300 particles (10 words: two staged row rounds, six words loaded on demand by
+    # the emission), cells below the 256 that move a handle to the row masks
+    L, n = 20.0, 21600
+    q = np.zeros((n, 4))
+    q[:, :3] = rng.random((n, 3)) * L
+    got = gpu_build(cuda, q, 3.3, (L,) * 3, "full_csr")
+    assert 96 < got["max_in_cell"] <= 256
+    assert_matches(oracle, got, oracle.build_full(q, 3.3, (L,) * 3))
+    # the same system with the words per run sized for 40 particles per cell: reported, grown, exact
+    nl = VerletListB200(3.3, L, L, L, mode="full_csr", max_in_cell=40)
+    nl.initialize(n)
+    qd = torch.from_numpy(q).cuda()
+    nl.build(qd)
+    with pytest.raises(NlistError) as e:
+        nl.synchronize()
+    assert e.value.status == _lib.ERR_CELL_CAPACITY
+    nl.reserve_cell_capacity(nl.stats().max_in_cell)
+    for _ in range(3):
+        nl.build(qd)
+        try:
+            st = nl.synchronize()
+            break
+        except NlistError as e2:
+            assert e2.status == _lib.ERR_CAPACITY
+            nl.reserve(nl.stats().required_entries)
+    got2 = {"np": nl.number_of_partners().cpu().numpy(), "off": nl.offsets().cpu().numpy(),
+            "list": nl.partners().cpu().numpy(), "pairs": st.number_of_pairs}
+    assert np.array_equal(got2["list"], got["list"]) and np.array_equal(got2["off"], got["off"])
+    nl.close()
+    qf = workloads.fcc(1.0, 30.0).astype(np.float32)
+    got = gpu_build(cuda, qf, 3.3, (30.0,) * 3, "full_csr", dtype="f32")
+    assert_matches(oracle, got, oracle.build_full(qf, 3.3, (30.0,) * 3))
+    # pairs within a few ulp of the search radius: the band re-test decides them exactly
+    SL, L, n0 = 3.3, 40.0, 3000
+    base = rng.random((n0, 3)) * (L - 8.0) + 4.0
+    dirs = rng.normal(size=(n0, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    q = np.zeros((2 * n0, 4))
+    q[:n0, :3] = base
+    q[n0:, :3] = base + dirs * (SL * (1.0 + rng.integers(-4, 5, size=(n0, 1)) * 2.0 ** -52))
+    got = gpu_build(cuda, q, SL, (L,) * 3, "full_csr")
+    assert got["band"] >= n0
+    assert_matches(oracle, got, oracle.build_full(q, SL, (L,) * 3))
+    exact = gpu_build(cuda, q, SL, (L,) * 3, "full_csr", exact_only=True)
+    assert np.array_equal(exact["np"], got["np"]) and np.array_equal(exact["list"], got["list"])
+    # owned subset + global ids (the rows a slab rank builds)
+    L = 24.0
+    q = workloads.fcc(1.0, L)
+    n = q.shape[0]
+    perm = rng.permutation(n).astype(np.int32)
+    n_owned = n // 3
+    ql = np.ascontiguousarray(q[perm])
+    nl = VerletListB200(3.3, L, L, L, mode="full_csr")
+    nl.initialize(n)
+    nl.build(torch.from_numpy(ql).cuda(), n_owned=n_owned, global_ids=torch.from_numpy(perm).cuda())
+    nl.synchronize()
+    ref = oracle.build_full(q, 3.3, (L, L, L)).sorted_rows()
+    off = nl.offsets().cpu().numpy()
+    lst = sort_rows(oracle, nl.partners().cpu().numpy(), off)
+    assert np.array_equal(nl.number_of_partners().cpu().numpy(), ref.number_of_partners[perm[:n_owned]])
+    for li in range(0, n_owned, 29):
+        g = perm[li]
+        assert np.array_equal(lst[off[li]:off[li + 1]], ref.partners[ref.offsets[g]:ref.offsets[g + 1]])
+    nl.close()
 
 
 def test_programmatic_dependent_launch_gives_the_same_list(cuda, oracle, monkeypatch):
