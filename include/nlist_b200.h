@@ -79,7 +79,11 @@ typedef enum {
   NLB200_OPT_EXACT_ONLY = 4,
   /* 1 (default): replay the build as a CUDA graph when (q, n, stream) repeat. 0: plain launches. */
   NLB200_OPT_USE_GRAPH = 5,
-  /* search-kernel variant selector for tuning/ablation (0 = default). */
+  /* search / emission pair, for tuning and ablation.  0 (default): run masks for FULL lists, pair masks for HALF
+   * lists, row masks once a cell may hold more than 256 particles.  1: one CTA per cell, every test evaluated twice
+   * (count, fill; also what NLB200_OPT_EXACT_ONLY runs).  2: pair masks.  4: pair masks, HALF rows filtered by id in
+   * the emission.  5, 6: row masks.  7: pair masks with 64-bit mask indices.  8: run masks.  100 + p: p work units
+   * per cell.  Every variant produces the same rows in the same order. */
   NLB200_OPT_KERNEL_VARIANT = 6,
   /* 1: record a CUDA event between the stages of every build on the build's stream (disables graph replay);
    * read the per-stage device times with nlb200_get_stage_times.  The reference's counterpart is
@@ -88,9 +92,11 @@ typedef enum {
   /* most particles one cell may hold — the reference's NMAX_IN_MESH (neighlist_gpu.hpp:74).  0 (default): estimated
    * from the mean occupancy at initialize (mean + 6 sigma).  Exceeding it is detected (NLB200_ERR_CELL_CAPACITY). */
   NLB200_OPT_MAX_IN_CELL = 8,
-  /* 1 (default): the kernels of a build are chained by programmatic dependent launch — a kernel's CTAs are scheduled
-   * while its predecessor drains and wait on the device for its results (no effect on the results).  0: plain
-   * stream order.  The environment variable NLB200_PDL=0/1 overrides the default at nlb200_create. */
+  /* 0 (default): the kernels of a build run in plain stream order (inside the replayed CUDA graph).  1: they are
+   * chained by programmatic dependent launch — a kernel's CTAs are scheduled while its predecessor drains and wait
+   * on the device for its results (no effect on the results; measured slower on the B200: 183 vs 172 us per build,
+   * DESIGN.md §5, so it is off unless asked for).  The environment variable NLB200_PDL=0/1 sets the default at
+   * nlb200_create. */
   NLB200_OPT_PDL = 9
 } nlb200_option;
 

@@ -225,9 +225,9 @@ void drop_graph(nlb200_context* h) {
 }
 
 // ---- launches of the build chain --------------------------------------------------------------------------------
-// With programmatic dependent launch (NLB200_OPT_PDL, default on) a kernel's CTAs are scheduled while its predecessor
-// drains and block in pdl_enter() until the predecessor's writes are visible: the launch latency of the nine small
-// kernels of a build is hidden, inside a captured graph (programmatic edges) as well as on a plain stream.
+// With programmatic dependent launch (NLB200_OPT_PDL, default OFF: measured slower) a kernel's CTAs are
+// scheduled while its predecessor drains and block in pdl_enter() until the predecessor's writes are visible, inside
+// a captured graph (programmatic edges) as well as on a plain stream.
 thread_local bool t_pdl = false;
 
 template <typename... KArgs, typename... Args>
@@ -274,9 +274,13 @@ constexpr int MAX_EMIT_SMEM = 200 * 1024;
 
 template <bool HALF, bool GID, bool COUNT>
 cudaError_t launch_emit_t(bool direct, const EmitArgs& a, cudaStream_t s) {
+#ifdef NLB_ABLATIONS
   if (direct)
     return launch_chain(emit_direct_kernel<HALF, GID, COUNT>, dim3((unsigned)((a.n_total + 127) / 128)), dim3(128), 0,
                         s, a);
+#else
+  (void)direct;  // the direct-store emission is an ablation: built only with -DNLB_ABLATIONS
+#endif
   constexpr int rows = EM_WARPS * 32;
   return launch_chain(emit_kernel<HALF, GID, COUNT>, dim3((unsigned)((a.n_total + rows - 1) / rows)), dim3(rows),
                       (size_t)EM_WARPS * 32 * EM_LINE * sizeof(int32_t), s, a);

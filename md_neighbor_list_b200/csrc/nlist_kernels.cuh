@@ -222,9 +222,13 @@ __global__ void __launch_bounds__(256) bin_kernel(const T* __restrict__ q, int32
   // ---- the last CTA scans the histogram ----
   __shared__ bool is_last;
   __shared__ int32_t wsum[8], wmax[8];
-  __threadfence();  // this CTA's histogram updates are visible before its ticket
   __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) {
+    // one fence, after the barrier: it is cumulative over the CTA's histogram updates (a MEMBAR.SC by every thread
+    // was 30 % of the kernel's stall samples, profiles/r02_ncu_bin.txt)
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
@@ -1287,7 +1291,8 @@ __global__ void __launch_bounds__(128) rowcount_kernel(EmitArgs a) {
   a.counts[id] = cnt;
 }
 
-// emit_direct_kernel (ablation, NLB200_OPT_KERNEL_VARIANT = 3): thread = row, every hit stored straight to
+#ifdef NLB_ABLATIONS
+// emit_direct_kernel (ablation, NLB200_OPT_KERNEL_VARIANT = 3 of a -DNLB_ABLATIONS build): thread = row, every hit stored straight to
 // partners[offsets[id] + k] — a warp store touches 32 rows, 32 single-word partial-sector writes.  Measured on B200:
 // 144 us vs 101 us staged on the default system, 5.9 ms vs 1.7 ms at 2 M uniform particles.
 template <bool HALF, bool GID, bool COUNT>
@@ -1317,6 +1322,8 @@ __global__ void __launch_bounds__(128) emit_direct_kernel(EmitArgs a) {
   });
   if (COUNT) a.counts[id] = cnt;
 }
+
+#endif  // NLB_ABLATIONS
 
 // emit_kernel: thread = row, warp = 32 consecutive cell-sorted slots; warps are independent (no CTA barrier).
 //   Each lane expands the set bits of its row's words, MSB first (one FLO per bit), into its line of a

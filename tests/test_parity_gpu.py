@@ -684,8 +684,8 @@ def test_cell_capacity_overflow_is_detected_then_recovered(cuda, oracle):
 
 @pytest.mark.parametrize("mode", ["full_csr", "half_csr"])
 def test_kernel_variants_emit_identical_lists(cuda, oracle, mode):
-    """variant 1 = one CTA per cell, test evaluated twice; 2 = pair masks + staged emission; 3 = pair masks + direct
-    emission; 5 = row masks, CTA per cell; 6 = row masks, warp-autonomous units (the path crowded cells take).  Same
+    """variant 1 = one CTA per cell, test evaluated twice; 2 = pair masks + staged emission; 3 = the same (the
+    direct-store emission is an ablation of -DNLB_ABLATIONS builds); 5 = row masks, CTA per cell; 6 = row masks, warp-autonomous units (the path crowded cells take).  Same
     rows, same order (stencil order), same counts and offsets."""
     from md_neighbor_list_b200 import workloads
     q = workloads.fcc(1.0, 23.0)
