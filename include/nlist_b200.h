@@ -304,6 +304,15 @@ int nlb200_halo_wait(void* ctrl_dev, int faces, void* stream);
  * nlb200_pack_faces_p2p, nlb200_build_subset. */
 int nlb200_set_halo_sync(nlb200_handle h, void* ctrl_dev, void* peer_free_lo, void* peer_free_hi);
 int nlb200_halo_done(void* ctrl_dev, void* peer_free_lo, void* peer_free_hi, void* stream);
+/* Folds nlb200_pack_faces_p2p into every nlb200_build_subset of `h` that is given global ids and ghost slots (after
+ * nlb200_set_halo_sync; same arguments as nlb200_pack_faces_p2p, the records [0, n_owned) of the build are the ones
+ * packed): the binning kernel that reads an owned record also sends it if it lies beyond a cut, the neighbours' flags
+ * are raised by its last CTA, and the ghosts are binned by a second launch whose CTAs wait for this rank's own flags.
+ * A step is then ONE call, nlb200_build_subset — no separate pass over the positions, no packing launch.
+ * state_dev == NULL undoes it (so does nlb200_set_halo_sync(h, NULL, ...)). */
+int nlb200_set_halo_pack(nlb200_handle h, int axis, double cut_lo, double cut_hi, void* peer_q_lo, int32_t* peer_gid_lo,
+                         void* peer_q_hi, int32_t* peer_gid_hi, int64_t capacity, int64_t* out_counts_dev,
+                         void* state_dev, void* peer_ready_lo, void* peer_ready_hi);
 
 /* Bytes of workspace nlb200_select_slab / nlb200_pack_slab need for n particles. */
 int64_t nlb200_select_slab_workspace(int64_t n);

@@ -54,6 +54,8 @@ struct nlb200_context {
   void* halo_ctrl = nullptr;            // nlb200_set_halo_sync: control block + the neighbours' free flags
   void* halo_free_lo = nullptr;
   void* halo_free_hi = nullptr;
+  HaloPackArgs halo_pack{};              // nlb200_set_halo_pack: the exchange folded into the binning kernels
+  bool halo_pack_on = false;
   int path = 0;                         // PATH_*: which search / emission pair the handle runs (pick_path)
   bool state_clean = false;             // the zero region is all zero (left so by the last build's finalize_kernel)
   int sm_count = 148;
@@ -316,6 +318,7 @@ cudaError_t set_runmask_attrs() {
   if ((e = cudaFuncSetAttribute(runmask_kernel<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(runmask_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(runmask_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(emitwin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(emitrun_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM);
 }
 
@@ -363,13 +366,18 @@ cudaError_t launch_search(bool half, bool fill, bool exact, const SearchArgs<T>&
 //   1, or NLB200_OPT_EXACT_ONLY: search_kernel twice (count, fill): every test in the input precision if asked
 //   2, 3, 4, 7, 100..:           pair masks and their ablations
 //   5: row masks with the CTA-per-cell search (rowmask_kernel)      6, 20..39: row masks (rowmask4_kernel)
-//   8, or the default for FULL lists: RUN MASKS (runmask_kernel, emitrun_kernel; nlist_runmask.cuh)
+//   8, or the default for FULL lists: RUN MASKS (runmask_kernel, emitwin_kernel; nlist_runmask.cuh)
+//                emission: emitrun_kernel (ids gathered from global memory) below EMITWIN_MIN_PARTICLES particles,
+//                emitwin_kernel (ids through a shared-memory window) from there on;  9 / 10 force the one / the other
+//   200..299: run masks with (variant - 200) units per cell (tuning)
 enum { PATH_V1 = 1, PATH_PAIRMASK = 2, PATH_ROWMASK = 3, PATH_RUNMASK = 4 };
 constexpr int64_t PAIRMASK_MAX_CELL = 256;
+constexpr int32_t EMITWIN_MIN_PARTICLES = 1 << 20;
 int pick_path(const nlb200_context* h, int64_t max_in_cell) {
   if (h->exact_only != 0 || h->variant == 1) return PATH_V1;
   if (h->variant == 5 || h->variant == 6 || (h->variant >= 20 && h->variant < 40)) return PATH_ROWMASK;
-  if (h->variant != 0 && h->variant != 8) return PATH_PAIRMASK;
+  const bool rn_tuning = h->variant == 9 || h->variant == 10 || (h->variant >= 200 && h->variant < 300);
+  if (h->variant != 0 && h->variant != 8 && !rn_tuning) return PATH_PAIRMASK;
   if (max_in_cell > PAIRMASK_MAX_CELL) return PATH_ROWMASK;
   if (h->mode != NLB200_HALF_CSR) return PATH_RUNMASK;  // 36 bytes x words-per-run per particle, dense
   if (h->variant == 8) return PATH_PAIRMASK;
@@ -499,14 +507,34 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
   h->state_clean = false;
   CK(h, stage(ST_BIN));
   const bool scan_in_bin = n > 0 && M <= BIN_SCAN_MAX_CELLS;
-  if (n > 0) {
+  // a slab rank with nlb200_set_halo_pack: the owned records are binned AND sent by the first launch, the ghosts are
+  // binned by a second one that waits for the neighbours' flags (bin_kernel, HALO)
+  const bool fused_halo = h->halo_pack_on && gids != nullptr && n_owned > 0 && n_owned < n_total;
+  if (n > 0 && fused_halo) {
+    const int32_t no = (int32_t)n_owned;
+    bin_kernel<T, STRIDE, false, 1><<<(no + 255) / 256, 256, 0, s>>>(q, 0, no, no, gp, h->cell_count, h->cell_rank,
+                                                                     h->status_dev, h->cell_start, h->ticket, gids,
+                                                                     h->halo_pack);
+    CK(h, cudaGetLastError());
+    if (scan_in_bin)
+      bin_kernel<T, STRIDE, true, 2><<<(n - no + 255) / 256, 256, 0, s>>>(q, no, n, no, gp, h->cell_count, h->cell_rank,
+                                                                          h->status_dev, h->cell_start, h->ticket, gids,
+                                                                          h->halo_pack);
+    else
+      bin_kernel<T, STRIDE, false, 2><<<(n - no + 255) / 256, 256, 0, s>>>(q, no, n, no, gp, h->cell_count,
+                                                                           h->cell_rank, h->status_dev, h->cell_start,
+                                                                           h->ticket, gids, h->halo_pack);
+    CK(h, cudaGetLastError());
+  } else if (n > 0) {
     // first kernel of the chain: a plain launch
     if (scan_in_bin)
-      bin_kernel<T, STRIDE, true><<<(n + 255) / 256, 256, 0, s>>>(q, n, (int32_t)n_owned, gp, h->cell_count, h->cell_rank,
-                                                                  h->status_dev, h->cell_start, h->ticket);
+      bin_kernel<T, STRIDE, true><<<(n + 255) / 256, 256, 0, s>>>(q, 0, n, (int32_t)n_owned, gp, h->cell_count,
+                                                                  h->cell_rank, h->status_dev, h->cell_start, h->ticket,
+                                                                  gids, HaloPackArgs{});
     else
-      bin_kernel<T, STRIDE, false><<<(n + 255) / 256, 256, 0, s>>>(q, n, (int32_t)n_owned, gp, h->cell_count,
-                                                                   h->cell_rank, h->status_dev, h->cell_start, h->ticket);
+      bin_kernel<T, STRIDE, false><<<(n + 255) / 256, 256, 0, s>>>(q, 0, n, (int32_t)n_owned, gp, h->cell_count,
+                                                                   h->cell_rank, h->status_dev, h->cell_start, h->ticket,
+                                                                   gids, HaloPackArgs{});
     CK(h, cudaGetLastError());
   }
   CK(h, stage(ST_SCAN_CELLS));
@@ -654,7 +682,8 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
       int64_t parts = (int64_t)(9.0 * ((double)n / (double)M) * 1.1 / (double)RN_CH + 0.999);
       if (parts < 1) parts = 1;
       if (parts > 16) parts = 16;
-      if (h->variant >= 100 && h->variant < 200) parts = h->variant - 100;  // tuning override
+      if (h->variant >= 200 && h->variant < 300) parts = h->variant - 200;  // tuning override
+      if (parts < 1) parts = 1;
       rn.parts = (int32_t)parts;
       int64_t grab = (M * parts) / (resident * 64);
       if (grab < 1) grab = 1;
@@ -695,8 +724,15 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
       em.partners = h->partners;
       em.capacity = h->cap_entries;
       constexpr int rows = ER_WARPS * 32;
-      CK(h, launch_chain(emitrun_kernel, dim3((unsigned)((n + rows - 1) / rows)), dim3(rows),
-                         (size_t)rows * EM_LINE * sizeof(int32_t), s, em));
+      // partner ids through a shared-memory window once the slot -> id table is far larger than an SM's L1 (the
+      // gather of emitrun_kernel then misses: 2 M uniform particles 1.10 -> 1.00 ms of emission); small systems keep
+      // the gather (default system: 61.7 us vs 69 us — the window adds an LDS to the expansion loop's chain)
+      const bool win = h->variant == 10 || (h->variant != 9 && n >= EMITWIN_MIN_PARTICLES);
+      if (!win)
+        CK(h, launch_chain(emitrun_kernel, dim3((unsigned)((n + rows - 1) / rows)), dim3(rows),
+                           (size_t)rows * EM_LINE * sizeof(int32_t), s, em));
+      else
+        CK(h, launch_chain(emitwin_kernel, dim3((unsigned)((n + rows - 1) / rows)), dim3(rows), ew_smem_bytes(), s, em));
     }
   } else if (use_v1) {
     // --- v1: one CTA per cell, thread per particle, test evaluated twice (count, fill).  Kept for the exact-only
@@ -1766,15 +1802,58 @@ int nlb200_pack_faces_p2p(const void* q_dev, const int32_t* gids_dev, int64_t n,
   HaloCtrl* ctrl = reinterpret_cast<HaloCtrl*>(ctrl_dev);
   unsigned long long* rl = reinterpret_cast<unsigned long long*>(peer_ready_lo);
   unsigned long long* rh = reinterpret_cast<unsigned long long*>(peer_ready_hi);
+  HaloPackArgs hp{};
+  hp.axis = axis;
+  hp.cut_lo = cut_lo;
+  hp.cut_hi = cut_hi;
+  hp.out_q_lo = peer_q_lo;
+  hp.out_gid_lo = peer_gid_lo;
+  hp.out_q_hi = peer_q_hi;
+  hp.out_gid_hi = peer_gid_hi;
+  hp.capacity = capacity;
+  hp.state = st;
+  hp.out_counts = reinterpret_cast<long long*>(out_counts_dev);
+  hp.ctrl = ctrl;
+  hp.peer_ready_lo = rl;
+  hp.peer_ready_hi = rh;
   if (dtype == NLB200_F64)
-    pack_faces_p2p_kernel<double><<<g, 256, 0, s>>>((const double*)q_dev, gids_dev, n, stride, axis, cut_lo, cut_hi,
-                                                   (double*)peer_q_lo, peer_gid_lo, (double*)peer_q_hi, peer_gid_hi,
-                                                   capacity, st, out_counts_dev, ctrl, rl, rh);
+    pack_faces_p2p_kernel<double><<<g, 256, 0, s>>>((const double*)q_dev, gids_dev, n, stride, hp);
   else
-    pack_faces_p2p_kernel<float><<<g, 256, 0, s>>>((const float*)q_dev, gids_dev, n, stride, axis, cut_lo, cut_hi,
-                                                  (float*)peer_q_lo, peer_gid_lo, (float*)peer_q_hi, peer_gid_hi,
-                                                  capacity, st, out_counts_dev, ctrl, rl, rh);
+    pack_faces_p2p_kernel<float><<<g, 256, 0, s>>>((const float*)q_dev, gids_dev, n, stride, hp);
   return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
+}
+
+int nlb200_set_halo_pack(nlb200_handle h, int axis, double cut_lo, double cut_hi, void* peer_q_lo, int32_t* peer_gid_lo,
+                         void* peer_q_hi, int32_t* peer_gid_hi, int64_t capacity, int64_t* out_counts_dev,
+                         void* state_dev, void* peer_ready_lo, void* peer_ready_hi) {
+  if (!h) return NLB200_ERR_INVALID;
+  if (h->build_pending && h->last_stream) CK(h, cudaStreamSynchronize(h->last_stream));
+  drop_graph(h);  // the arguments are captured with the binning kernels
+  if (!state_dev) {  // undo
+    h->halo_pack_on = false;
+    h->halo_pack = HaloPackArgs{};
+    return NLB200_OK;
+  }
+  if (!h->halo_ctrl) return fail(h, NLB200_ERR_STATE, "nlb200_set_halo_pack needs nlb200_set_halo_sync first");
+  if (axis < 0 || axis > 2 || capacity < 0 || !out_counts_dev)
+    return fail(h, NLB200_ERR_INVALID, "nlb200_set_halo_pack: bad argument");
+  HaloPackArgs hp{};
+  hp.axis = axis;
+  hp.cut_lo = cut_lo;
+  hp.cut_hi = cut_hi;
+  hp.out_q_lo = peer_q_lo;
+  hp.out_gid_lo = peer_gid_lo;
+  hp.out_q_hi = peer_q_hi;
+  hp.out_gid_hi = peer_gid_hi;
+  hp.capacity = capacity;
+  hp.state = reinterpret_cast<unsigned long long*>(state_dev);
+  hp.out_counts = reinterpret_cast<long long*>(out_counts_dev);
+  hp.ctrl = reinterpret_cast<HaloCtrl*>(h->halo_ctrl);
+  hp.peer_ready_lo = reinterpret_cast<unsigned long long*>(peer_ready_lo);
+  hp.peer_ready_hi = reinterpret_cast<unsigned long long*>(peer_ready_hi);
+  h->halo_pack = hp;
+  h->halo_pack_on = true;
+  return NLB200_OK;
 }
 
 int nlb200_set_halo_sync(nlb200_handle h, void* ctrl_dev, void* peer_free_lo, void* peer_free_hi) {
@@ -1783,6 +1862,10 @@ int nlb200_set_halo_sync(nlb200_handle h, void* ctrl_dev, void* peer_free_lo, vo
   h->halo_ctrl = ctrl_dev;
   h->halo_free_lo = ctrl_dev ? peer_free_lo : nullptr;
   h->halo_free_hi = ctrl_dev ? peer_free_hi : nullptr;
+  if (!ctrl_dev) {
+    h->halo_pack_on = false;
+    h->halo_pack = HaloPackArgs{};
+  }
   drop_graph(h);  // the pointers are arguments of the captured finalize_kernel
   return NLB200_OK;
 }

@@ -166,6 +166,61 @@ __device__ __forceinline__ bool exact_within(const Vec3<float>& a, const Vec3<fl
   return !(r2 > sl2);
 }
 
+// ---- halo exchange by peer stores: control block and flags (protocol: see pack_faces_p2p_kernel below) ----
+struct HaloCtrl {
+  unsigned long long step;          // steps completed by this rank
+  unsigned long long ready[2];      // [0]: ghosts from the lower neighbour are complete for step ready[0]; [1]: upper
+  unsigned long long free_from[2];  // [0]: the lower neighbour has finished reading what this rank sent it; [1]: upper
+  unsigned long long error;         // a bounded wait gave up
+  unsigned long long pad[2];
+};
+constexpr unsigned int HALO_SPIN_LIMIT = 1u << 26;  // ~1 s of polling, then give up
+
+__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// values only THIS rank writes (its step counter, its error word): a volatile load from the L2 — no acquire needed
+__device__ __forceinline__ unsigned long long ld_own(const unsigned long long* p) {
+  return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+// a flag store that follows a __threadfence_system() of the same thread: the fence already ordered the data before it
+__device__ __forceinline__ void st_sys_relaxed(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// returns false if the flag did not reach `want` within the spin limit
+__device__ __forceinline__ bool halo_wait_flag(const unsigned long long* flag, unsigned long long want) {
+  for (unsigned int spins = 0; spins < HALO_SPIN_LIMIT; spins++) {
+    if (ld_sys(flag) >= want) return true;
+    __nanosleep(64);
+  }
+  return false;
+}
+
+// What a slab rank sends and where (nlb200_pack_faces_p2p / nlb200_set_halo_pack).
+struct HaloPackArgs {
+  int axis;
+  double cut_lo, cut_hi;      // a record with q[axis] < cut_lo goes to the lower neighbour, >= cut_hi to the upper
+  void* out_q_lo;             // the neighbours' ghost regions (peer pointers); nullptr: no such neighbour
+  int32_t* out_gid_lo;
+  void* out_q_hi;
+  int32_t* out_gid_hi;
+  long long capacity;         // records per face region
+  unsigned long long* state;  // [0..1] cursors, [2] ticket, [3..4] previous counts
+  long long* out_counts;      // true counts of the step (> capacity = overflow)
+  HaloCtrl* ctrl;
+  unsigned long long* peer_ready_lo;
+  unsigned long long* peer_ready_hi;
+};
+
+template <typename T, bool WAIT_OWN>
+__device__ __forceinline__ void halo_pack_cta(const T* __restrict__ q, const int32_t* __restrict__ gids, int64_t i,
+                                              int64_t n, int stride, const HaloPackArgs& hp);
+
 // ---------------------------------------------------------------------------------------------------------------
 // 1. cell index + histogram
 // ---------------------------------------------------------------------------------------------------------------
@@ -179,13 +234,28 @@ __device__ __forceinline__ bool exact_within(const Vec3<float>& a, const Vec3<fl
 // crowded cell — one kernel boundary less for grids of up to BIN_SCAN_MAX_CELLS cells (the separate look-back scan
 // serves larger grids: one CTA needs ~1 us per thousand cells).  For the default system (3375 cells) one CTA scans in ~2 us what cost a launch of its own.
 constexpr int BIN_SCAN_MAX_CELLS = 1 << 13;
-template <typename T, int STRIDE, bool SCAN_HERE>
-__global__ void __launch_bounds__(256) bin_kernel(const T* __restrict__ q, int32_t n, int32_t n_owned,
+// HALO (a slab rank whose exchange is folded into its build, nlb200_set_halo_pack): the build bins in two launches.
+//   HALO = 1, records [0, n_owned): the CTA that bins an owned record also SENDS it if it lies within the search
+//             length of a face (halo_pack_cta: peer stores into the neighbour's ghost region; the last CTA raises the
+//             neighbours' `ready` flags) — the separate packing kernel, its pass over the positions and its launch
+//             are gone, and the flight of the flags over NVLink overlaps the kernel boundary;
+//   HALO = 2, records [n_owned, n): every CTA first waits for this rank's own `ready` flags, then bins the ghosts.
+template <typename T, int STRIDE, bool SCAN_HERE, int HALO = 0>
+__global__ void __launch_bounds__(256) bin_kernel(const T* __restrict__ q, int32_t i0, int32_t n, int32_t n_owned,
                                                   GridParams<T> gp, int32_t* __restrict__ cell_count,
                                                   int2* __restrict__ cell_rank, DeviceStatus* __restrict__ st,
-                                                  int32_t* __restrict__ cell_start, unsigned int* __restrict__ ticket) {
+                                                  int32_t* __restrict__ cell_start, unsigned int* __restrict__ ticket,
+                                                  const int32_t* __restrict__ gids, HaloPackArgs hp) {
   pdl_enter();
-  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (HALO == 2) {
+    if (threadIdx.x < 2) {  // lane f waits for face f: both acquire loads in flight together
+      const unsigned long long want = ld_own(&hp.ctrl->step) + 1ull;
+      const bool face = threadIdx.x == 0 ? hp.out_q_lo != nullptr : hp.out_q_hi != nullptr;
+      if (face && !halo_wait_flag(&hp.ctrl->ready[threadIdx.x], want)) hp.ctrl->error = 1ull;
+    }
+    __syncthreads();  // orders every thread's ghost loads after the two acquires
+  }
   if (i < n) {
     const Vec3<T> p = load_pos<T, STRIDE>(q, i);
     if (i >= n_owned && p.x != p.x) {
@@ -218,6 +288,7 @@ __global__ void __launch_bounds__(256) bin_kernel(const T* __restrict__ q, int32
       cell_rank[i] = make_int2(cell, rank);
     }
   }
+  if (HALO == 1) halo_pack_cta<T, false>(q, gids, (int64_t)i, (int64_t)n, STRIDE, hp);
   if (!SCAN_HERE) return;
   // ---- the last CTA scans the histogram ----
   __shared__ bool is_last;
@@ -1805,42 +1876,24 @@ __global__ void __launch_bounds__(256) pack_faces_kernel(const T* __restrict__ q
 //   receiver (halo_wait_kernel before the build):   wait ready[f] >= n for both faces
 //            (finalize_kernel after the build):     step = n; set neighbour.free_from[f'] = n
 // ---------------------------------------------------------------------------------------------------------------
-struct HaloCtrl {
-  unsigned long long step;          // steps completed by this rank
-  unsigned long long ready[2];      // [0]: ghosts from the lower neighbour are complete for step ready[0]; [1]: upper
-  unsigned long long free_from[2];  // [0]: the lower neighbour has finished reading what this rank sent it; [1]: upper
-  unsigned long long error;         // a bounded wait gave up
-  unsigned long long pad[2];
-};
-constexpr unsigned int HALO_SPIN_LIMIT = 1u << 26;  // ~1 s of polling, then give up
-
-__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// returns false if the flag did not reach `want` within the spin limit
-__device__ __forceinline__ bool halo_wait_flag(const unsigned long long* flag, unsigned long long want) {
-  for (unsigned int spins = 0; spins < HALO_SPIN_LIMIT; spins++) {
-    if (ld_sys(flag) >= want) return true;
-    __nanosleep(64);
-  }
-  return false;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) pack_faces_p2p_kernel(const T* __restrict__ q, const int32_t* __restrict__ gids,
-                                                             int64_t n, int stride, int axis, double cut_lo,
-                                                             double cut_hi, T* out_q_lo, int32_t* out_gid_lo,
-                                                             T* out_q_hi, int32_t* out_gid_hi, int64_t capacity,
-                                                             unsigned long long* __restrict__ state,
-                                                             int64_t* __restrict__ out_counts, HaloCtrl* ctrl,
-                                                             unsigned long long* peer_ready_lo,
-                                                             unsigned long long* peer_ready_hi) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+// The packing step of one CTA of 256 threads (thread <-> record i; i >= n: no record).  Called by every thread of
+// every CTA of the launch exactly once; the last CTA to arrive pads, signals the neighbours and — WAIT_OWN — waits for
+// this rank's own ghosts.
+template <typename T, bool WAIT_OWN>
+__device__ __forceinline__ void halo_pack_cta(const T* __restrict__ q, const int32_t* __restrict__ gids, int64_t i,
+                                              int64_t n, int stride, const HaloPackArgs& hp) {
+  const int axis = hp.axis;
+  const double cut_lo = hp.cut_lo, cut_hi = hp.cut_hi;
+  T* out_q_lo = reinterpret_cast<T*>(hp.out_q_lo);
+  T* out_q_hi = reinterpret_cast<T*>(hp.out_q_hi);
+  int32_t* out_gid_lo = hp.out_gid_lo;
+  int32_t* out_gid_hi = hp.out_gid_hi;
+  const int64_t capacity = hp.capacity;
+  unsigned long long* state = hp.state;
+  long long* out_counts = hp.out_counts;
+  HaloCtrl* ctrl = hp.ctrl;
+  unsigned long long* peer_ready_lo = hp.peer_ready_lo;
+  unsigned long long* peer_ready_hi = hp.peer_ready_hi;
   const int lane = threadIdx.x & 31;
   __shared__ bool is_last, go;
   bool f_lo = false, f_hi = false;
@@ -1852,15 +1905,20 @@ __global__ void __launch_bounds__(256) pack_faces_p2p_kernel(const T* __restrict
   // only a CTA that has something to send touches the neighbours: it first makes sure that they have finished
   // reading what the previous step wrote into them
   const bool sends = __syncthreads_or(f_lo || f_hi) != 0;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    // lanes 0..2 read {step, free_from[0], free_from[1]} together: three system-scope loads in flight at once instead
+    // of one after the other (each is a round trip to the L2)
     bool ok = true;
     if (sends) {
-      const unsigned long long step = ld_sys(&ctrl->step);
-      if (out_q_lo != nullptr) ok = halo_wait_flag(&ctrl->free_from[0], step) && ok;
-      if (out_q_hi != nullptr) ok = halo_wait_flag(&ctrl->free_from[1], step) && ok;
-      if (!ok) ctrl->error = 1ull;
+      unsigned long long v = 0ull;
+      if (lane < 3) v = lane == 0 ? ld_own(&ctrl->step) : ld_sys(&ctrl->free_from[lane - 1]);
+      const unsigned long long step = __shfl_sync(0xffffffffu, v, 0);
+      const bool face = (lane == 1 && out_q_lo != nullptr) || (lane == 2 && out_q_hi != nullptr);
+      if (face && v < step) ok = halo_wait_flag(&ctrl->free_from[lane - 1], step);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok && lane == 0) ctrl->error = 1ull;
     }
-    go = ok;
+    if (lane == 0) go = ok;
   }
   __syncthreads();
   if (!go) f_lo = f_hi = false;
@@ -1889,10 +1947,16 @@ __global__ void __launch_bounds__(256) pack_faces_p2p_kernel(const T* __restrict
       og[pos] = gids != nullptr ? gids[i] : (int32_t)i;
     }
   }
-  if (sends) __threadfence_system();  // this CTA's peer stores are visible system-wide before its ticket
-  __threadfence();
+  // ONE fence per CTA, after the barrier: it is cumulative over the stores of the CTA's threads (the barrier orders
+  // them before it), system-wide if the CTA wrote into a neighbour — a fence by every thread was most of the kernel
   __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(&state[2], 1ull) == (unsigned long long)gridDim.x - 1ull;
+  if (threadIdx.x == 0) {
+    if (sends)
+      __threadfence_system();  // this CTA's peer stores are visible system-wide before its ticket
+    else
+      __threadfence();
+    is_last = atomicAdd(&state[2], 1ull) == (unsigned long long)gridDim.x - 1ull;
+  }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
@@ -1902,12 +1966,12 @@ __global__ void __launch_bounds__(256) pack_faces_p2p_kernel(const T* __restrict
   // absent slots: the regions start out all-NaN (the owner fills them once), so only the slots that held a record of
   // the PREVIOUS step and hold none now have to be cleared (state[3], state[4] remember the previous counts)
   const long long p_lo = (long long)state[3], p_hi = (long long)state[4];
-  if (threadIdx.x == 0) go = ld_sys(&ctrl->error) == 0ull;  // some CTA gave up waiting: nothing more is sent
+  if (threadIdx.x == 0) go = ld_own(&ctrl->error) == 0ull;  // some CTA gave up waiting: nothing more is sent
   __syncthreads();
   if (go && (c_lo < p_lo || c_hi < p_hi) && threadIdx.x == 0) {
     // slots are about to be cleared in the neighbours: they must have finished the previous step (a CTA that sent
     // records has checked this already; this one may not have sent any)
-    const unsigned long long step = ld_sys(&ctrl->step);
+    const unsigned long long step = ld_own(&ctrl->step);
     bool ok = true;
     if (out_q_lo != nullptr) ok = halo_wait_flag(&ctrl->free_from[0], step) && ok;
     if (out_q_hi != nullptr) ok = halo_wait_flag(&ctrl->free_from[1], step) && ok;
@@ -1923,9 +1987,9 @@ __global__ void __launch_bounds__(256) pack_faces_p2p_kernel(const T* __restrict
     for (int64_t t = min(c_hi, (long long)capacity) * stride + threadIdx.x; t < min(p_hi, (long long)capacity) * stride;
          t += blockDim.x)
       out_q_hi[t] = nan;
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();  // cumulative over the CTA's clearing stores (ordered before it by the barrier)
     out_counts[0] = c_lo;
     out_counts[1] = c_hi;
     state[0] = state[1] = state[2] = 0ull;
@@ -1933,16 +1997,25 @@ __global__ void __launch_bounds__(256) pack_faces_p2p_kernel(const T* __restrict
       state[3] = (unsigned long long)c_lo;
       state[4] = (unsigned long long)c_hi;
     }
-    const unsigned long long nstep = ld_sys(&ctrl->step) + 1ull;
-    if (go && peer_ready_lo != nullptr) st_sys(peer_ready_lo, nstep);
-    if (go && peer_ready_hi != nullptr) st_sys(peer_ready_hi, nstep);
-    // ... and this rank's own ghosts: wait here for the neighbours' flags, so that the build can follow directly
-    bool ok = go;
-    if (ok && out_q_lo != nullptr) ok = halo_wait_flag(&ctrl->ready[0], nstep);
-    if (ok && out_q_hi != nullptr) ok = halo_wait_flag(&ctrl->ready[1], nstep) && ok;
-    if (!ok) ctrl->error = 1ull;
-    __threadfence_system();
+    const unsigned long long nstep = ld_own(&ctrl->step) + 1ull;
+    // (the system-scope fence above ordered every record and padding store of the grid before these two flags)
+    if (go && peer_ready_lo != nullptr) st_sys_relaxed(peer_ready_lo, nstep);
+    if (go && peer_ready_hi != nullptr) st_sys_relaxed(peer_ready_hi, nstep);
+    if (WAIT_OWN) {
+      // ... and this rank's own ghosts: wait here for the neighbours' flags, so that the build can follow directly
+      bool ok = go;
+      if (ok && out_q_lo != nullptr) ok = halo_wait_flag(&ctrl->ready[0], nstep);
+      if (ok && out_q_hi != nullptr) ok = halo_wait_flag(&ctrl->ready[1], nstep) && ok;
+      if (!ok) ctrl->error = 1ull;
+      __threadfence_system();
+    }
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_faces_p2p_kernel(const T* __restrict__ q, const int32_t* __restrict__ gids,
+                                                             int64_t n, int stride, HaloPackArgs hp) {
+  halo_pack_cta<T, true>(q, gids, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, n, stride, hp);
 }
 
 // before the build of a slab rank: the ghosts of both faces have arrived (faces: bit 0 lower, bit 1 upper)

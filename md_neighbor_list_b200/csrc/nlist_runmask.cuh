@@ -554,4 +554,204 @@ __global__ void __launch_bounds__(ER_WARPS * 32, NLB_ER_MINB) emitrun_kernel(Emi
   flush(true);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// emission from run masks, partner ids through a shared-memory WINDOW.  Same decomposition as emitrun_kernel (thread =
+// row, warp = 32 consecutive cell-sorted slots, lines of the warp's tile flushed by their own lanes), but the
+// slot -> partner id translation happens where the bit is expanded: the 32 rows of a warp share, for a given run
+// ordinal, at most a few neighbouring cells, so the ids of every slot their run can name form ONE contiguous piece of
+// slot_pid (~140 ids on the default system).  The warp stages that piece once per run (coalesced), the expansion loop
+// reads the id with an LDS and the lines hold final ids: the flush is a plain copy (no per-entry gather from global
+// memory — in emitrun_kernel 16 M LDG whose lanes all name different cache lines: 12.5 % of the L1 data-pipe
+// wavefronts and the long-scoreboard stalls of its flush).  Warps whose window does not fit (rows that straddle the
+// end of a cell row, crowded cells) take the same loop with the id read from global memory.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef NLB_EW_WIN
+#define NLB_EW_WIN 192
+#endif
+constexpr int EW_WIN = NLB_EW_WIN;
+#ifndef NLB_EW_MINB
+#define NLB_EW_MINB 13
+#endif
+__host__ __device__ inline size_t ew_smem_bytes() {
+  return (size_t)ER_WARPS * (32 * EM_LINE + EW_WIN) * sizeof(int32_t);
+}
+
+__global__ void __launch_bounds__(ER_WARPS * 32, NLB_EW_MINB) emitwin_kernel(EmitRunArgs a) {
+  pdl_enter();
+  extern __shared__ __align__(16) int32_t er_smem[];
+  if (a.offsets[a.n_owned] > a.capacity) return;  // overflow already flagged by the offsets scan
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  int32_t* line = er_smem + (warp * 32 + lane) * EM_LINE;
+  int32_t* win = er_smem + ER_WARPS * 32 * EM_LINE + warp * EW_WIN;
+  const int32_t slot = (blockIdx.x * ER_WARPS + warp) * 32 + lane;
+  int32_t id = 0x7fffffff;
+  if (slot < a.n_total && slot < __ldg(a.cell_start + a.n_cells)) id = __ldg(a.sorted_ids + slot);
+  const bool owned = id < a.n_owned;
+  if (!__any_sync(0xffffffffu, owned)) return;
+  const int32_t cell = owned ? __ldg(a.slot_cell + slot) : 0;
+  const long long dst = owned ? (long long)a.offsets[id] : 0;
+  int32_t fill = 0;  // entries staged in this lane's line
+  int32_t done = 0;  // entries of this row already written
+
+  // Every lane copies ITS OWN line (final ids) to its row: scalar stores until the row position is 32-byte aligned,
+  // then one STG.256 per 8 entries; what does not fill a vector stays in the line.
+  auto flush = [&](bool final) {
+    int32_t k = 0;
+    int32_t* out = a.partners + dst + done;
+    while (k < fill && ((reinterpret_cast<uintptr_t>(out + k) & 31) != 0)) {
+      out[k] = line[k];
+      k++;
+    }
+    while (k + 8 <= fill) {
+      int32_t v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = line[k + u];
+      asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(out + k), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                   "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                   : "memory");
+      k += 8;
+    }
+    if (final) {
+      while (k < fill) {
+        out[k] = line[k];
+        k++;
+      }
+    }
+    done += k;
+    const int32_t left = fill - k;
+    for (int32_t t = 0; t < left; t++) line[t] = line[k + t];
+    fill = left;
+  };
+
+  const int32_t mx = a.mesh[0], my = a.mesh[1], mz = a.mesh[2];
+  const int32_t byz = (int32_t)fdiv((uint32_t)cell, a.d_mx), bx = cell - byz * mx;
+  const int32_t bz = (int32_t)fdiv((uint32_t)byz, a.d_my), by = byz - bz * my;
+  int xlo, xhi, ylo, yhi, zlo, zhi;
+  axis_range(bx, mx, xlo, xhi);
+  axis_range(by, my, ylo, yhi);
+  axis_range(bz, mz, zlo, zhi);
+  const int32_t ny = yhi - ylo + 1, nz = zhi - zlo + 1;
+  const uint32_t* mrow = a.mask + min((long long)slot, a.n_cap - 1);  // lanes past the last slot load in range
+  const long long run_stride = (long long)a.wr * a.n_cap;  // words between the planes of two runs
+  const int32_t pre = min(a.wr, ER_PRE);
+
+  // Bit position p of a word <-> the slot `last - p` (last = the slot of bit 0).  In the window: the id sits at the
+  // shared-memory byte address last_sa - 4 p.  Two entries per trip, the second predicated; both id loads are issued
+  // before the first store into the line, so a trip waits for shared memory once.
+  const uint32_t line_sa = (uint32_t)__cvta_generic_to_shared(line);
+  const uint32_t win_sa = (uint32_t)__cvta_generic_to_shared(win);
+  auto expand_win = [&](uint32_t word, uint32_t last_sa) {
+    uint32_t wa = line_sa + 4u * (uint32_t)fill;
+    fill += __popc(word);
+    if (word) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p, q;\n\t"
+          ".reg .u32 pos, bit, ad, v0, v1;\n"
+          "EXPANDW_%=:\n\t"
+          "bfind.u32 pos, %0;\n\t"
+          "shl.b32 bit, 1, pos;\n\t"
+          "mad.lo.s32 ad, pos, -4, %2;\n\t"
+          "xor.b32 %0, %0, bit;\n\t"
+          "ld.shared.s32 v0, [ad];\n\t"
+          "setp.ne.u32 p, %0, 0;\n\t"
+          "@p bfind.u32 pos, %0;\n\t"
+          "@p shl.b32 bit, 1, pos;\n\t"
+          "@p mad.lo.s32 ad, pos, -4, %2;\n\t"
+          "@p xor.b32 %0, %0, bit;\n\t"
+          "@p ld.shared.s32 v1, [ad];\n\t"
+          "st.shared.s32 [%1], v0;\n\t"
+          "@p st.shared.s32 [%1+4], v1;\n\t"
+          "add.u32 %1, %1, 8;\n\t"
+          "setp.ne.u32 q, %0, 0;\n\t"
+          "@q bra EXPANDW_%=;\n\t"
+          "}"
+          : "+r"(word), "+r"(wa)
+          : "r"(last_sa)
+          : "memory");
+    }
+  };
+  // the same with the id read from global memory (warps without a window)
+  auto expand_glb = [&](uint32_t word, const int32_t* last) {
+    int32_t* wp = line + fill;
+    fill += __popc(word);
+    while (word) {
+      const int p = 31 - __clz(word);
+      word ^= 1u << p;
+      *wp++ = __ldg(last - p);
+    }
+  };
+  auto expand = [&](uint32_t word, const int32_t* glb_last, uint32_t sa_last, bool in_smem) {
+    if (in_smem)
+      expand_win(word, sa_last);
+    else
+      expand_glb(word, glb_last);
+  };
+  int32_t s0n, s1n;
+  uint32_t mn[ER_PRE];
+  const uint32_t* mrun = mrow;
+  auto request = [&](int r) {
+    const int oz = r / 3, oy = r - oz * 3;
+    const int32_t* cs = a.cell_start + (min(ylo + oy, my - 1) + min(zlo + oz, mz - 1) * my) * mx;
+    s0n = __ldg(cs + xlo);
+    s1n = __ldg(cs + xhi + 1);
+#pragma unroll
+    for (int u = 0; u < ER_PRE; u++) mn[u] = __ldg(mrun + (long long)min(u, pre - 1) * a.n_cap);
+    mrun += run_stride;
+  };
+  request(0);
+#pragma unroll 1
+  for (int r = 0; r < 9; r++) {
+    const int oz = r / 3, oy = r - oz * 3;
+    const int32_t s0 = s0n, s1 = s1n;
+    const bool rv = owned && (oz < nz) && (oy < ny);
+    const int32_t nw = rv ? min((s1 - s0 + 31) >> 5, a.wr) : 0;  // > wr only after FLAG_CELL_WORDS
+    uint32_t m[ER_PRE];
+    int32_t tot = 0;
+#pragma unroll
+    for (int u = 0; u < ER_PRE; u++) {
+      m[u] = u < nw ? mn[u] : 0u;
+      tot += __popc(m[u]);
+    }
+    if (r < 8) request(r + 1);
+    const int32_t nwmax = __reduce_max_sync(0xffffffffu, nw);
+    if (nwmax == 0) continue;
+    // the window: every slot a row of this warp can name in this run
+    const int32_t w0 = __reduce_min_sync(0xffffffffu, nw > 0 ? s0 : 0x7fffffff);
+    const int32_t w1 = __reduce_max_sync(0xffffffffu, nw > 0 ? min(s1, s0 + 32 * nw) : 0);
+    const bool in_smem = w1 - w0 <= EW_WIN;
+    if (in_smem) {
+      __syncwarp();  // the previous run's readers are done
+      for (int32_t k = lane; k < w1 - w0; k += 32) win[k] = __ldg(a.slot_pid + w0 + k);
+      __syncwarp();
+    }
+    const int32_t* src = a.slot_pid + s0 + 31;
+    const uint32_t ssa = win_sa + 4u * (uint32_t)(s0 - w0 + 31);
+    if (__any_sync(0xffffffffu, fill + tot > EM_TILE)) flush(false);  // leaves fill <= 7
+    if (!__any_sync(0xffffffffu, tot > EM_TILE - 7 || nw > ER_PRE)) {
+      // the run fits the line: no check between its words
+#pragma unroll
+      for (int u = 0; u < ER_PRE; u++)
+        if (u < nwmax) expand(m[u], src + 32 * u, ssa + 128u * u, in_smem);
+    } else {
+      // a long run (the row's own run can hold more partners than a line, crowded cells more than ER_PRE words):
+      // word by word with a check before each — the requested words from their registers, the rest on demand
+#pragma unroll
+      for (int u = 0; u < ER_PRE; u++) {
+        if (u < nwmax && __any_sync(0xffffffffu, m[u] != 0u)) {
+          if (__any_sync(0xffffffffu, fill + __popc(m[u]) > EM_TILE)) flush(false);
+          expand(m[u], src + 32 * u, ssa + 128u * u, in_smem);
+        }
+      }
+      for (int32_t w = ER_PRE; w < nwmax; w++) {
+        const uint32_t word = w < nw ? __ldg(mrow + ((long long)(r * a.wr + w)) * a.n_cap) : 0u;
+        if (!__any_sync(0xffffffffu, word != 0u)) continue;
+        if (__any_sync(0xffffffffu, fill + __popc(word) > EM_TILE)) flush(false);
+        expand(word, src + 32 * w, ssa + 128u * (uint32_t)w, in_smem);
+      }
+    }
+  }
+  flush(true);
+}
+
 }  // namespace nlb

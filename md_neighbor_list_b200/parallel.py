@@ -30,6 +30,8 @@ is injected by the caller (`build_fn`) and is the CUDA library in the product.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -396,7 +398,22 @@ class PeerSlabDecomposition(SlabDecomposition):
             return base + p["o_g"] + slot * 4
         return base + {"ready0": 8, "ready1": 16, "free0": 24, "free1": 32}[what]
 
-    def exchange(self, q_owned: torch.Tensor, gid_owned: torch.Tensor):
+    def _pack_args(self):
+        """(cut_lo, cut_hi, peer regions, capacity, counts, state, ready flags) — what nlb200_pack_faces_p2p and
+        nlb200_set_halo_pack are told: my lower-face particles go into the lower neighbour's "ghosts from above"
+        region (second region), my upper-face particles into the upper neighbour's "ghosts from below" region."""
+        p = self._p2p
+        lo_p, hi_p = p["peers"].get(self.rank - 1), p["peers"].get(self.rank + 1)
+        cap, n_cap = p["cap"], p["n_cap"]
+        return (self.lo + self.sl if lo_p else -float("inf"), self.hi - self.sl if hi_p else float("inf"),
+                self._addr(lo_p, "q", n_cap + cap) if lo_p else None, self._addr(lo_p, "g", n_cap + cap) if lo_p else None,
+                self._addr(hi_p, "q", n_cap) if hi_p else None, self._addr(hi_p, "g", n_cap) if hi_p else None,
+                cap, self._cnt2.data_ptr(), self._state.data_ptr(),
+                self._addr(lo_p, "ready1") if lo_p else None, self._addr(hi_p, "ready0") if hi_p else None)
+
+    def exchange(self, q_owned: torch.Tensor, gid_owned: torch.Tensor, launch: bool = True):
+        """launch=False: only place the owned records and return the assembly buffers — the build of a handle with
+        nlb200_set_halo_pack packs, sends and waits itself (build())."""
         if self.world == 1 or not q_owned.is_cuda:
             return super().exchange(q_owned, gid_owned)
         n = q_owned.shape[0]
@@ -409,20 +426,14 @@ class PeerSlabDecomposition(SlabDecomposition):
             self._gall[:n].copy_(gid_owned)
         L = _lib.lib()
         lo_p, hi_p = p["peers"].get(self.rank - 1), p["peers"].get(self.rank + 1)
-        cap, n_cap = p["cap"], p["n_cap"]
         dtype = _lib.F64 if q_owned.dtype == torch.float64 else _lib.F32
         s = torch.cuda.current_stream().cuda_stream
-        # my lower-face particles go into the lower neighbour's "ghosts from above" region (second region), my
-        # upper-face particles into the upper neighbour's "ghosts from below" region (first region)
-        st = L.nlb200_pack_faces_p2p(
-            self._qall.data_ptr(), self._gall.data_ptr(), n, dtype, self.stride, self.axis,
-            self.lo + self.sl if lo_p else -float("inf"), self.hi - self.sl if hi_p else float("inf"),
-            self._addr(lo_p, "q", n_cap + cap) if lo_p else None, self._addr(lo_p, "g", n_cap + cap) if lo_p else None,
-            self._addr(hi_p, "q", n_cap) if hi_p else None, self._addr(hi_p, "g", n_cap) if hi_p else None,
-            cap, self._cnt2.data_ptr(), self._state.data_ptr(), p["base"],
-            self._addr(lo_p, "ready1") if lo_p else None, self._addr(hi_p, "ready0") if hi_p else None, s)
-        if st != _lib.OK:
-            raise _lib.NlistError(st, "nlb200_pack_faces_p2p failed")
+        if launch:
+            a = self._pack_args()
+            st = L.nlb200_pack_faces_p2p(self._qall.data_ptr(), self._gall.data_ptr(), n, dtype, self.stride, self.axis,
+                                         a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], p["base"], a[9], a[10], s)
+            if st != _lib.OK:
+                raise _lib.NlistError(st, "nlb200_pack_faces_p2p failed")
         # (the packing kernel ends by waiting for this rank's own ghosts: no separate nlb200_halo_wait launch)
         self._cnt = {}
         if lo_p:
@@ -449,7 +460,15 @@ class PeerSlabDecomposition(SlabDecomposition):
         with ctx:
             if gid_owned is None:
                 gid_owned = self.global_ids(q_owned.shape[0], q_owned.device)
-            q_all, gid_all, n_owned = self.exchange(q_owned, gid_owned)
+            # the library's own build of a peer-store decomposition packs, sends and waits inside its binning kernels
+            # (nlb200_set_halo_pack; NLB_HALO_FUSED=0: the separate packing kernel)
+            fused = (build_fn is None and self.world > 1 and q_owned.is_cuda
+                     and os.environ.get("NLB_HALO_FUSED", "1") != "0"
+                     and self._setup(q_owned.shape[0], q_owned.dtype, q_owned.device))
+            if fused:
+                q_all, gid_all, n_owned = self.exchange(q_owned, gid_owned, launch=False)
+            else:
+                q_all, gid_all, n_owned = self.exchange(q_owned, gid_owned)
             if build_fn is not None:
                 out = build_fn(q_all, n_owned, gid_all)
             else:
@@ -460,6 +479,10 @@ class PeerSlabDecomposition(SlabDecomposition):
                     _lib.check(nl._h, _lib.lib().nlb200_set_halo_sync(
                         nl._h, p["base"], self._addr(lo_p, "free1") if lo_p else None,
                         self._addr(hi_p, "free0") if hi_p else None))
+                    if fused:
+                        a = self._pack_args()
+                        _lib.check(nl._h, _lib.lib().nlb200_set_halo_pack(
+                            nl._h, self.axis, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10]))
                     self._synced_handle = nl
                 nl.build(q_all, n_owned=n_owned, global_ids=gid_all if self.world > 1 else None, stream=stream)
                 out = None
