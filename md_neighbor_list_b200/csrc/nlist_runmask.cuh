@@ -637,7 +637,8 @@ __global__ void __launch_bounds__(ER_WARPS * 32, NLB_EW_MINB) emitwin_kernel(Emi
 
   // Bit position p of a word <-> the slot `last - p` (last = the slot of bit 0).  In the window: the id sits at the
   // shared-memory byte address last_sa - 4 p.  Two entries per trip, the second predicated; both id loads are issued
-  // before the first store into the line, so a trip waits for shared memory once.
+  // before the first store into the line, so a trip waits for shared memory once.  (Four entries per trip: 88 bytes
+  // of spills at 72 registers, 2^24 uniform particles 8.27 -> 9.12 ms.)
   const uint32_t line_sa = (uint32_t)__cvta_generic_to_shared(line);
   const uint32_t win_sa = (uint32_t)__cvta_generic_to_shared(win);
   auto expand_win = [&](uint32_t word, uint32_t last_sa) {

@@ -693,7 +693,9 @@ def test_kernel_variants_emit_identical_lists(cuda, oracle, mode):
     # 4 = HALF rows filtered by id during the emission (the multi-GPU path) instead of inside the masks
     # 7 = mask indices in 64-bit arithmetic (the path of systems whose masks exceed 2^32 words)
     # 8 = run masks (the default of FULL lists; HALF lists fall back to the pair masks)
-    outs = [gpu_build(cuda, q, 3.3, box, mode, kernel_variant=v) for v in (1, 2, 3, 4, 7, 5, 6, 8, 0)]
+    # 9 / 10 = run masks with the emission that gathers partner ids from global memory / reads them through a
+    #          shared-memory window (the default picks by system size)
+    outs = [gpu_build(cuda, q, 3.3, box, mode, kernel_variant=v) for v in (1, 2, 3, 4, 7, 5, 6, 8, 0, 9, 10)]
     for o in outs[1:]:
         assert o["pairs"] == outs[0]["pairs"]
         assert np.array_equal(o["np"], outs[0]["np"])
@@ -768,12 +770,15 @@ def test_row_mask_path_on_every_input_class(cuda, oracle, variant):
         nl.close()
 
 
-def test_run_mask_path_on_every_input_class(cuda, oracle):
+@pytest.mark.parametrize("variant", [9, 10])
+def test_run_mask_path_on_every_input_class(cuda, oracle, variant):
     """The run-mask search + emission (FULL lists' default: rows of an x-run as bits, the column's particles on the
     lanes; nlist_runmask.cuh) on the inputs that exercise its special cases: 3-cell axes (runs and columns cover the
     whole axis), empty cells and runs, runs of more words than the emission requests ahead (> 128 particles) and of
     more than one staged row round (> 256), the words-per-run capacity grown after a failed build, FP32 positions,
-    pairs on the search radius, duplicates, owned subsets with a global-id map, stencil order of the rows."""
+    pairs on the search radius, duplicates, owned subsets with a global-id map, stencil order of the rows.
+    variant 9: emitrun_kernel (ids gathered from global memory, the default below 2^20 particles); 10: emitwin_kernel
+    (ids through a shared-memory window; the ~300-particle runs here exceed the window and take its global fallback)."""
     from md_neighbor_list_b200 import NlistError, VerletListB200, _lib, workloads
     torch = cuda
     rng = np.random.default_rng(11)
@@ -781,24 +786,24 @@ def test_run_mask_path_on_every_input_class(cuda, oracle):
     q = np.zeros((5000, 4))
     q[:, :3] = rng.random((5000, 3)) * np.array(box)
     q[150:170, :3] = q[170:190, :3]  # duplicates: r2 == 0 (only the row's own bit is dropped)
-    got = gpu_build(cuda, q, 3.3, box, "full_csr")
+    got = gpu_build(cuda, q, 3.3, box, "full_csr", kernel_variant=variant)
     assert_matches(oracle, got, oracle.bruteforce(q, 3.3, full=True))
     ref = oracle.build_full(q, 3.3, box)
     assert np.array_equal(got["list"], ref.partners)  # rows in stencil order: the reference kernels' discovery order
     q = np.zeros((300, 4))
     q[:, :3] = rng.random((300, 3)) * 60.0
-    got = gpu_build(cuda, q, 3.3, (60.0,) * 3, "full_csr")
+    got = gpu_build(cuda, q, 3.3, (60.0,) * 3, "full_csr", kernel_variant=variant)
     assert_matches(oracle, got, oracle.bruteforce(q, 3.3, full=True))
     # ~100 particles per cell: runs of ~300 particles (10 words: two staged row rounds, six words loaded on demand by
     # the emission), cells below the 256 that move a handle to the row masks
     L, n = 20.0, 21600
     q = np.zeros((n, 4))
     q[:, :3] = rng.random((n, 3)) * L
-    got = gpu_build(cuda, q, 3.3, (L,) * 3, "full_csr")
+    got = gpu_build(cuda, q, 3.3, (L,) * 3, "full_csr", kernel_variant=variant)
     assert 96 < got["max_in_cell"] <= 256
     assert_matches(oracle, got, oracle.build_full(q, 3.3, (L,) * 3))
     # the same system with the words per run sized for 40 particles per cell: reported, grown, exact
-    nl = VerletListB200(3.3, L, L, L, mode="full_csr", max_in_cell=40)
+    nl = VerletListB200(3.3, L, L, L, mode="full_csr", max_in_cell=40, kernel_variant=variant)
     nl.initialize(n)
     qd = torch.from_numpy(q).cuda()
     nl.build(qd)
@@ -819,7 +824,7 @@ def test_run_mask_path_on_every_input_class(cuda, oracle):
     assert np.array_equal(got2["list"], got["list"]) and np.array_equal(got2["off"], got["off"])
     nl.close()
     qf = workloads.fcc(1.0, 30.0).astype(np.float32)
-    got = gpu_build(cuda, qf, 3.3, (30.0,) * 3, "full_csr", dtype="f32")
+    got = gpu_build(cuda, qf, 3.3, (30.0,) * 3, "full_csr", dtype="f32", kernel_variant=variant)
     assert_matches(oracle, got, oracle.build_full(qf, 3.3, (30.0,) * 3))
     # pairs within a few ulp of the search radius: the band re-test decides them exactly
     SL, L, n0 = 3.3, 40.0, 3000
@@ -829,7 +834,7 @@ def test_run_mask_path_on_every_input_class(cuda, oracle):
     q = np.zeros((2 * n0, 4))
     q[:n0, :3] = base
     q[n0:, :3] = base + dirs * (SL * (1.0 + rng.integers(-4, 5, size=(n0, 1)) * 2.0 ** -52))
-    got = gpu_build(cuda, q, SL, (L,) * 3, "full_csr")
+    got = gpu_build(cuda, q, SL, (L,) * 3, "full_csr", kernel_variant=variant)
     assert got["band"] >= n0
     assert_matches(oracle, got, oracle.build_full(q, SL, (L,) * 3))
     exact = gpu_build(cuda, q, SL, (L,) * 3, "full_csr", exact_only=True)
@@ -841,7 +846,7 @@ def test_run_mask_path_on_every_input_class(cuda, oracle):
     perm = rng.permutation(n).astype(np.int32)
     n_owned = n // 3
     ql = np.ascontiguousarray(q[perm])
-    nl = VerletListB200(3.3, L, L, L, mode="full_csr")
+    nl = VerletListB200(3.3, L, L, L, mode="full_csr", kernel_variant=variant)
     nl.initialize(n)
     nl.build(torch.from_numpy(ql).cuda(), n_owned=n_owned, global_ids=torch.from_numpy(perm).cuda())
     nl.synchronize()
@@ -881,6 +886,23 @@ def test_cpp_driver_self_test(cuda, iface, dens):
     assert r.returncode == 0, r.stderr
     assert "TEST is passed." in r.stderr
     assert "# of particles 62500" in r.stdout
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_cpp_driver_slab_ranks(cuda, world):
+    """drivers/make_list_b200.cpp slab G: the multi-GPU build from a C++ host through the C ABI alone —
+    G processes (one per GPU; on a box with fewer GPUs they share devices, the device-side flags still order the
+    steps), CUDA IPC handles passed over pipes, the halo exchange folded into nlb200_build_subset
+    (nlb200_set_halo_sync / nlb200_set_halo_pack), five replays of each rank's graph, every rank's rows against an
+    O(N^2) brute force over the global system."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "drivers", "make_list_b200.out")
+    if not os.path.exists(exe):
+        pytest.fail("drivers/make_list_b200.out is missing: run __graft_entry__.build()")
+    r = subprocess.run([exe, "slab", str(world), "1.0", "5"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "TEST is passed." in r.stderr
+    assert r.stdout.count("owned particles") == world
 
 
 def test_cpp_driver_md_loop(cuda):
