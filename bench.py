@@ -665,7 +665,10 @@ def run_ours(args):
 
     halo_transport = None
     if halo is not None:
-        halo_transport = ("ghost exchange by peer stores of the packing kernel (CUDA IPC over NVLink), no NCCL call "
+        halo_transport = ("ghost exchange by peer stores of the build's binning kernel (CUDA IPC over NVLink; "
+                          "nlb200_set_halo_pack), no NCCL call and no packing launch on the step"
+                          if getattr(halo, "uses_peer_stores", lambda: False)() and os.environ.get("NLB_HALO_FUSED", "1") != "0"
+                          else "ghost exchange by peer stores of the packing kernel (CUDA IPC over NVLink), no NCCL call "
                           "on the step" if getattr(halo, "uses_peer_stores", lambda: False)()
                           else "ghost exchange by one grouped NCCL send/recv")
         if hasattr(halo, "close"):
@@ -738,7 +741,8 @@ def run_ours(args):
                              + ", ".join(f"{k}={v:.1f}" for k, v in times.items()),
                    "ms_per_build": times, "host_nproc": os.cpu_count()}
         # kernels of one build: bin (+ cell scan), scatter, cellsort, runmask, scan(counts), emitrun, finalize
-        # (+ the halo packing of a slab rank: one kernel)
+        # (a slab rank: the binning kernel runs twice — owned records + halo send, then the ghosts — or, with
+        #  NLB_HALO_FUSED=0 / NCCL, one packing kernel precedes the build: one more launch either way)
         kernels_per_build = 7 if world == 1 else 7 + 1
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
