@@ -323,7 +323,7 @@ int slab_rank(int rank, int world, double density, int loop, const Pipes& io) {
         peer[0] ? reinterpret_cast<int32_t*>(peer[0] + o_g + (n_cap + cap) * 4) : nullptr,
         peer[1] ? peer[1] + o_q + n_cap * 32 : nullptr,
         peer[1] ? reinterpret_cast<int32_t*>(peer[1] + o_g + n_cap * 4) : nullptr, cap, counts, state,
-        ctrl_of(peer[0], 2), ctrl_of(peer[1], 1)));
+        ctrl_of(peer[0], 2), ctrl_of(peer[1], 1), nullptr, nullptr));
   }
   const auto t0 = std::chrono::steady_clock::now();
   for (int k = 0; k < loop; k++) {

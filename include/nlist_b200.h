@@ -312,7 +312,17 @@ int nlb200_halo_done(void* ctrl_dev, void* peer_free_lo, void* peer_free_hi, voi
  * state_dev == NULL undoes it (so does nlb200_set_halo_sync(h, NULL, ...)). */
 int nlb200_set_halo_pack(nlb200_handle h, int axis, double cut_lo, double cut_hi, void* peer_q_lo, int32_t* peer_gid_lo,
                          void* peer_q_hi, int32_t* peer_gid_hi, int64_t capacity, int64_t* out_counts_dev,
-                         void* state_dev, void* peer_ready_lo, void* peer_ready_hi);
+                         void* state_dev, void* peer_ready_lo, void* peer_ready_hi, int32_t* send_idx_lo_dev,
+                         int32_t* send_idx_hi_dev);
+/* Incremental halo refresh (the drivers' 100 identical rebuilds, make_list.cpp:153-155, stand for
+ * the MD steps a list survives): between two builds the list stays valid while nlb200_max_displacement <= margin / 2,
+ * but its consumer needs the CURRENT positions of the ghosts.  With send_idx_lo_dev / send_idx_hi_dev given to
+ * nlb200_set_halo_pack (capacity int32 each, or NULL: no recording) every build records which owned record went into
+ * which ghost slot; nlb200_halo_refresh re-sends exactly those records of q_dev into the same slots of the neighbours
+ * (no selection, no compaction; global ids and the list stay as they are), raises the neighbours' flags and waits for
+ * this rank's own ghosts.  It is one step of the flag protocol: every rank calls it, consumes its ghosts, then ends the
+ * step with nlb200_halo_done(ctrl, peer_free_lo, peer_free_hi, stream). */
+int nlb200_halo_refresh(nlb200_handle h, const void* q_dev, void* stream);
 
 /* Bytes of workspace nlb200_select_slab / nlb200_pack_slab need for n particles. */
 int64_t nlb200_select_slab_workspace(int64_t n);

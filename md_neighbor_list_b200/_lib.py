@@ -77,7 +77,8 @@ SYMBOLS = {
     "nlb200_halo_wait": (C.c_int, [_vp, _i32, _vp]),
     "nlb200_set_halo_sync": (C.c_int, [_vp, _vp, _vp, _vp]),
     "nlb200_halo_done": (C.c_int, [_vp, _vp, _vp, _vp]),
-    "nlb200_set_halo_pack": (C.c_int, [_vp, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "nlb200_set_halo_pack": (C.c_int, [_vp, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nlb200_halo_refresh": (C.c_int, [_vp, _vp, _vp]),
     "nlb200_select_slab_workspace": (_i64, [_i64]),
     "nlb200_shift_axis": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _dbl, _vp]),
     "nlb200_gather_records": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),

@@ -1825,7 +1825,8 @@ int nlb200_pack_faces_p2p(const void* q_dev, const int32_t* gids_dev, int64_t n,
 
 int nlb200_set_halo_pack(nlb200_handle h, int axis, double cut_lo, double cut_hi, void* peer_q_lo, int32_t* peer_gid_lo,
                          void* peer_q_hi, int32_t* peer_gid_hi, int64_t capacity, int64_t* out_counts_dev,
-                         void* state_dev, void* peer_ready_lo, void* peer_ready_hi) {
+                         void* state_dev, void* peer_ready_lo, void* peer_ready_hi, int32_t* send_idx_lo_dev,
+                         int32_t* send_idx_hi_dev) {
   if (!h) return NLB200_ERR_INVALID;
   if (h->build_pending && h->last_stream) CK(h, cudaStreamSynchronize(h->last_stream));
   drop_graph(h);  // the arguments are captured with the binning kernels
@@ -1851,9 +1852,27 @@ int nlb200_set_halo_pack(nlb200_handle h, int axis, double cut_lo, double cut_hi
   hp.ctrl = reinterpret_cast<HaloCtrl*>(h->halo_ctrl);
   hp.peer_ready_lo = reinterpret_cast<unsigned long long*>(peer_ready_lo);
   hp.peer_ready_hi = reinterpret_cast<unsigned long long*>(peer_ready_hi);
+  hp.send_idx_lo = send_idx_lo_dev;
+  hp.send_idx_hi = send_idx_hi_dev;
   h->halo_pack = hp;
   h->halo_pack_on = true;
   return NLB200_OK;
+}
+
+int nlb200_halo_refresh(nlb200_handle h, const void* q_dev, void* stream) {
+  if (!h || !q_dev) return NLB200_ERR_INVALID;
+  if (!h->halo_pack_on || !h->halo_pack.send_idx_lo || !h->halo_pack.send_idx_hi)
+    return fail(h, NLB200_ERR_STATE, "nlb200_halo_refresh needs nlb200_set_halo_pack with send-index buffers");
+  if (!h->have_build) return fail(h, NLB200_ERR_STATE, "nlb200_halo_refresh before the first build");
+  (void)cudaGetLastError();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t cap = h->halo_pack.capacity > 0 ? h->halo_pack.capacity : 1;
+  const unsigned g = (unsigned)((cap + 255) / 256);
+  if (h->dtype == NLB200_F64)
+    halo_refresh_kernel<double><<<g, 256, 0, s>>>((const double*)q_dev, h->stride, h->halo_pack);
+  else
+    halo_refresh_kernel<float><<<g, 256, 0, s>>>((const float*)q_dev, h->stride, h->halo_pack);
+  return cudaGetLastError() == cudaSuccess ? NLB200_OK : NLB200_ERR_CUDA;
 }
 
 int nlb200_set_halo_sync(nlb200_handle h, void* ctrl_dev, void* peer_free_lo, void* peer_free_hi) {

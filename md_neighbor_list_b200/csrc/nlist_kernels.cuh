@@ -215,6 +215,8 @@ struct HaloPackArgs {
   HaloCtrl* ctrl;
   unsigned long long* peer_ready_lo;
   unsigned long long* peer_ready_hi;
+  int32_t* send_idx_lo;       // optional [capacity]: the local index of the record packed into slot k of the face —
+  int32_t* send_idx_hi;       // the recorded face set nlb200_halo_refresh re-sends between two builds
 };
 
 template <typename T, bool WAIT_OWN>
@@ -1945,6 +1947,8 @@ __device__ __forceinline__ void halo_pack_cta(const T* __restrict__ q, const int
         for (int c = 0; c < stride; c++) oq[pos * stride + c] = q[i * stride + c];
       }
       og[pos] = gids != nullptr ? gids[i] : (int32_t)i;
+      int32_t* sidx = f == 0 ? hp.send_idx_lo : hp.send_idx_hi;
+      if (sidx != nullptr) sidx[pos] = (int32_t)i;
     }
   }
   // ONE fence per CTA, after the barrier: it is cumulative over the stores of the CTA's threads (the barrier orders
@@ -2016,6 +2020,75 @@ template <typename T>
 __global__ void __launch_bounds__(256) pack_faces_p2p_kernel(const T* __restrict__ q, const int32_t* __restrict__ gids,
                                                              int64_t n, int stride, HaloPackArgs hp) {
   halo_pack_cta<T, true>(q, gids, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, n, stride, hp);
+}
+
+// Incremental halo refresh: between two builds a Verlet list stays valid while no particle has
+// moved more than margin / 2, but a consumer of the list needs the CURRENT positions of the ghosts.  The face set of
+// the last build is recorded (send_idx: slot k of a face <- local record send_idx[k]); this kernel re-sends exactly
+// those records into the same slots of the neighbours' ghost regions — no selection, no compaction, ids untouched —
+// under the same flag protocol as a packing step: wait until the neighbour has finished with the previous contents,
+// peer stores, one system fence per CTA, the last CTA raises the neighbours' `ready` flags and waits for this rank's
+// own.  The caller consumes the ghosts and ends the step with nlb200_halo_done.
+template <typename T>
+__global__ void __launch_bounds__(256) halo_refresh_kernel(const T* __restrict__ q, int stride, HaloPackArgs hp) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  __shared__ bool is_last, go;
+  HaloCtrl* ctrl = hp.ctrl;
+  const long long n_lo = hp.out_q_lo != nullptr ? min(hp.out_counts[0], hp.capacity) : 0;
+  const long long n_hi = hp.out_q_hi != nullptr ? min(hp.out_counts[1], hp.capacity) : 0;
+  const bool f_lo = t < n_lo, f_hi = t < n_hi;
+  const bool sends = __syncthreads_or(f_lo || f_hi) != 0;
+  if (threadIdx.x < 32) {
+    bool ok = true;
+    if (sends) {
+      unsigned long long v = 0ull;
+      if (lane < 3) v = lane == 0 ? ld_own(&ctrl->step) : ld_sys(&ctrl->free_from[lane - 1]);
+      const unsigned long long step = __shfl_sync(0xffffffffu, v, 0);
+      const bool face = (lane == 1 && hp.out_q_lo != nullptr) || (lane == 2 && hp.out_q_hi != nullptr);
+      if (face && v < step) ok = halo_wait_flag(&ctrl->free_from[lane - 1], step);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok && lane == 0) ctrl->error = 1ull;
+    }
+    if (lane == 0) go = ok;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int f = 0; f < 2; f++) {
+    if (!(f == 0 ? f_lo : f_hi) || !go) continue;
+    const int64_t i = (f == 0 ? hp.send_idx_lo : hp.send_idx_hi)[t];
+    T* oq = reinterpret_cast<T*>(f == 0 ? hp.out_q_lo : hp.out_q_hi);
+    if (stride == 4 && sizeof(T) == 8) {
+      const double2* src = reinterpret_cast<const double2*>(q + i * 4);
+      double2* dst = reinterpret_cast<double2*>(oq + t * 4);
+      dst[0] = src[0];
+      dst[1] = src[1];
+    } else {
+      for (int c = 0; c < stride; c++) oq[t * stride + c] = q[i * stride + c];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (sends)
+      __threadfence_system();
+    else
+      __threadfence();
+    is_last = atomicAdd(&hp.state[2], 1ull) == (unsigned long long)gridDim.x - 1ull;
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  hp.state[2] = 0ull;
+  const bool good = ld_own(&ctrl->error) == 0ull;
+  __threadfence_system();
+  const unsigned long long nstep = ld_own(&ctrl->step) + 1ull;
+  if (good && hp.peer_ready_lo != nullptr) st_sys_relaxed(hp.peer_ready_lo, nstep);
+  if (good && hp.peer_ready_hi != nullptr) st_sys_relaxed(hp.peer_ready_hi, nstep);
+  bool ok = good;
+  if (ok && hp.out_q_lo != nullptr) ok = halo_wait_flag(&ctrl->ready[0], nstep);
+  if (ok && hp.out_q_hi != nullptr) ok = halo_wait_flag(&ctrl->ready[1], nstep) && ok;
+  if (!ok) ctrl->error = 1ull;
+  __threadfence_system();
 }
 
 // before the build of a slab rank: the ghosts of both faces have arrived (faces: bit 0 lower, bit 1 upper)

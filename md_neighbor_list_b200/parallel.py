@@ -371,6 +371,7 @@ class PeerSlabDecomposition(SlabDecomposition):
         self._ctrl = torch.as_tensor(_DevArray(base.value, (8,), "<i8"), device=dev)
         self._state = torch.zeros(8, dtype=torch.int64, device=dev)  # cursors, ticket, previous counts
         self._cnt2 = torch.zeros(2, dtype=torch.int64, device=dev)
+        self._send_idx = torch.zeros((2, max(cap, 1)), dtype=torch.int32, device=dev)  # the recorded face set (refresh)
         torch.cuda.synchronize()
         dist.barrier(group=self.group)  # nobody writes into a neighbour before it has initialised its buffer
         return True
@@ -482,13 +483,30 @@ class PeerSlabDecomposition(SlabDecomposition):
                     if fused:
                         a = self._pack_args()
                         _lib.check(nl._h, _lib.lib().nlb200_set_halo_pack(
-                            nl._h, self.axis, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10]))
+                            nl._h, self.axis, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10],
+                            self._send_idx[0].data_ptr(), self._send_idx[1].data_ptr()))
                     self._synced_handle = nl
                 nl.build(q_all, n_owned=n_owned, global_ids=gid_all if self.world > 1 else None, stream=stream)
                 out = None
             if q_owned.is_cuda and self.world > 1 and (build_fn is not None or not self.uses_peer_stores()):
                 self.done()
         return out
+
+    def refresh(self, nl, q_owned: torch.Tensor, stream=None):
+        """Incremental halo refresh: between two builds, re-send the CURRENT positions of the face set
+        the last build of `nl` recorded into the same ghost slots of the neighbours and wait for this rank's own ghosts
+        (nlb200_halo_refresh).  Every rank calls it; returns the assembly buffers (owned records + refreshed ghosts).
+        After consuming the ghosts call done() — the neighbours may then overwrite them."""
+        if not (self.uses_peer_stores() and self._synced_handle is nl):
+            raise _lib.NlistError(_lib.ERR_STATE, "refresh() needs a build of this handle with the folded exchange first")
+        n = q_owned.shape[0]
+        ctx = torch.cuda.stream(stream) if stream is not None else _null()
+        with ctx:
+            if q_owned.data_ptr() != self._qall.data_ptr():
+                self._qall[:n].copy_(q_owned)
+            _lib.check(nl._h, _lib.lib().nlb200_halo_refresh(nl._h, self._qall.data_ptr(),
+                                                             torch.cuda.current_stream().cuda_stream))
+        return self._qall, self._gall, n
 
     def uses_peer_stores(self) -> bool:
         return bool(self._p2p and self._p2p.get("ok"))

@@ -3,7 +3,9 @@
 EVERY rank builds the rows of its slab with the CUDA library — exchange folded into the build (nlb200_set_halo_pack)
 and with the separate packing kernel (NLB_HALO_FUSED=0) — for several steps between which the particles MOVE (so the
 face populations and the ghost counts change and stale ghost slots must be cleared), and compares counts, offsets and
-row-sorted partners with the oracle run on the global system.  Rank 0 prints HALO ROWS OK."""
+row-sorted partners with the oracle run on the global system; then the incremental halo refresh (nlb200_halo_refresh):
+the recorded face set re-sent at new positions, every ghost slot against the neighbour's current record.  Rank 0 prints
+HALO ROWS OK."""
 import os
 import sys
 
@@ -74,6 +76,41 @@ for fused in ("1", "0"):
             ok = False
             print(f"rank {rank} fused={fused} step {step}: rows differ from the oracle", flush=True)
             break
+    if ok and fused == "1":
+        # incremental halo refresh: the particles move a little (the list would stay valid), the face
+        # set recorded by the last build is re-sent: every ghost slot must hold the CURRENT position of its global id,
+        # unused slots stay absent, global ids are untouched; a build afterwards continues the flag protocol
+        qa0, _, no0 = halo.last_assembled()
+        present0 = ~np.isnan(qa0.cpu().numpy()[:, 0])
+        present0[:no0] = False
+        for rep in range(2):
+            q_new = q_now.copy()
+            q_new[:, :2] = np.clip(q_new[:, :2] + (rep + 1) * 0.05 * vel[:, :2], 0.0, np.array(box[:2]) - 1e-9)
+            q_dev.copy_(torch.from_numpy(np.ascontiguousarray(q_new[own])))
+            torch.cuda.synchronize()
+            dist.barrier()
+            qa, ga, no = halo.refresh(nl, q_dev, s)
+            s.synchronize()
+            halo.check()
+            qh, gh = qa.cpu().numpy(), ga.cpu().numpy()
+            halo.done()
+            present = ~np.isnan(qh[:, 0])
+            present[:no] = False
+            if not np.array_equal(present, present0) or not np.array_equal(qh[present], q_new[gh[present]]):
+                ok = False
+                print(f"rank {rank}: refreshed ghosts differ from the neighbours' current positions", flush=True)
+                break
+        if ok:
+            q_dev.copy_(torch.from_numpy(np.ascontiguousarray(q_new[own])))
+            torch.cuda.synchronize()
+            dist.barrier()
+            halo.build(nl, q_dev, s, gid_owned=gid_dev)
+            nl.synchronize()
+            halo.check()
+            ref = O.build_full(np.ascontiguousarray(q_new), SL, box).sorted_rows()
+            if not np.array_equal(nl.number_of_partners().cpu().numpy(), ref.number_of_partners[own]):
+                ok = False
+                print(f"rank {rank}: build after the refresh differs from the oracle", flush=True)
     nl.close()
     halo.close()
 t = torch.tensor([1 if ok else 0], device=dev)
