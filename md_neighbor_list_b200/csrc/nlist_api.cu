@@ -92,6 +92,8 @@ struct nlb200_context {
   unsigned long long* disp_dev = nullptr;
   unsigned long long* disp_host = nullptr;  // pinned
   cudaStream_t own_stream = nullptr;
+  cudaStream_t side_stream = nullptr;  // second branch of a build's graph (finalize_kernel beside the emission)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   // host mirrors
   DeviceStatus* status_host = nullptr;  // pinned
@@ -210,6 +212,11 @@ void free_buffers(nlb200_context* h) {
   h->status_host = nullptr;
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   h->own_stream = nullptr;
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  h->side_stream = nullptr;
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  h->ev_fork = h->ev_join = nullptr;
   for (int k = 0; k <= nlb200_context::MAX_STAGES; k++) {
     if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     h->ev[k] = nullptr;
@@ -573,6 +580,30 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
   }
   const bool half = h->mode == NLB200_HALF_CSR;
   const bool use_v1 = uses_v1(h);
+  // finalize_kernel: status block to mapped host memory, per-build state re-zeroed, (slab ranks) the neighbours told
+  // that their ghosts may be overwritten
+  bool finalized_early = false;
+  auto launch_finalize = [&](cudaStream_t fs, bool chained) -> int {
+    const size_t vecs = h->zero_bytes / 16;
+    unsigned fgrid = (unsigned)((vecs + 1023) / 1024);
+    if (fgrid < 1) fgrid = 1;
+    if (fgrid > (unsigned)h->sm_count * 4) fgrid = (unsigned)h->sm_count * 4;
+    if (chained) {
+      CK(h, launch_chain(finalize_kernel, dim3(fgrid), dim3(256), 0, fs, h->status_dev, h->status_host,
+                         reinterpret_cast<uint4*>(h->zero_region), vecs, h->status_off / 16,
+                         (sizeof(DeviceStatus) + 15) / 16, reinterpret_cast<HaloCtrl*>(h->halo_ctrl),
+                         reinterpret_cast<unsigned long long*>(h->halo_free_lo),
+                         reinterpret_cast<unsigned long long*>(h->halo_free_hi)));
+    } else {
+      finalize_kernel<<<fgrid, 256, 0, fs>>>(h->status_dev, h->status_host, reinterpret_cast<uint4*>(h->zero_region),
+                                             vecs, h->status_off / 16, (sizeof(DeviceStatus) + 15) / 16,
+                                             reinterpret_cast<HaloCtrl*>(h->halo_ctrl),
+                                             reinterpret_cast<unsigned long long*>(h->halo_free_lo),
+                                             reinterpret_cast<unsigned long long*>(h->halo_free_hi));
+      CK(h, cudaGetLastError());
+    }
+    return NLB200_OK;
+  };
   if (uses_rowmask(h)) {
     // --- default: row masks.  Search (every test once, verdict blocks transposed to row-major words, row lengths
     //     on the way) -> offsets -> emission. ---
@@ -705,6 +736,18 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
                          h->status_dev, &h->status_dev->max_partners, (long long)h->cap_entries));
     }
     CK(h, stage(ST_EMITRUN));
+    // After the offsets scan nothing the status block reports can change any more on this path (the emission writes
+    // the list only) and every kernel that reads the ghosts has run: finalize_kernel becomes a second branch of the
+    // graph BESIDE the emission instead of a node behind it.
+    if (n > 0 && !h->profile && !t_pdl && !h->sort_rows && h->mode != NLB200_FULL_ELL_TRANSPOSED && s != nullptr &&
+        s != cudaStreamLegacy && s != cudaStreamPerThread) {
+      CK(h, cudaEventRecord(h->ev_fork, s));
+      CK(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+      const int rc_fin = launch_finalize(h->side_stream, false);
+      if (rc_fin) return rc_fin;
+      CK(h, cudaEventRecord(h->ev_join, h->side_stream));
+      finalized_early = true;
+    }
     if (n > 0) {
       EmitRunArgs em;
       em.cell_start = h->cell_start;
@@ -734,6 +777,7 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
       else
         CK(h, launch_chain(emitwin_kernel, dim3((unsigned)((n + rows - 1) / rows)), dim3(rows), ew_smem_bytes(), s, em));
     }
+    if (finalized_early) CK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
   } else if (use_v1) {
     // --- v1: one CTA per cell, thread per particle, test evaluated twice (count, fill).  Kept for the exact-only
     //     validation mode and as an ablation. ---
@@ -879,16 +923,9 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
                        h->ell_prev, (long long)h->cap_entries, h->status_dev));
   }
   CK(h, stage(ST_STATUS));
-  {
-    const size_t vecs = h->zero_bytes / 16;
-    unsigned fgrid = (unsigned)((vecs + 1023) / 1024);
-    if (fgrid < 1) fgrid = 1;
-    if (fgrid > (unsigned)h->sm_count * 4) fgrid = (unsigned)h->sm_count * 4;
-    CK(h, launch_chain(finalize_kernel, dim3(fgrid), dim3(256), 0, s, h->status_dev, h->status_host,
-                       reinterpret_cast<uint4*>(h->zero_region), vecs, h->status_off / 16,
-                       (sizeof(DeviceStatus) + 15) / 16, reinterpret_cast<HaloCtrl*>(h->halo_ctrl),
-                       reinterpret_cast<unsigned long long*>(h->halo_free_lo),
-                       reinterpret_cast<unsigned long long*>(h->halo_free_hi)));
+  if (!finalized_early) {
+    const int rc_fin = launch_finalize(s, true);
+    if (rc_fin) return rc_fin;
   }
   h->state_clean = true;
   if (h->profile) CK(h, cudaEventRecord(h->ev[h->n_stages], s));
@@ -1223,6 +1260,9 @@ int nlb200_initialize(nlb200_handle h, int64_t max_particles, int64_t max_entrie
   CK(h, cudaMallocHost(&h->status_host, sizeof(DeviceStatus)));
   memset(h->status_host, 0, sizeof(DeviceStatus));
   CK(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CK(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+  CK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   if (h->profile)
     for (int k = 0; k <= nlb200_context::MAX_STAGES; k++) CK(h, cudaEventCreate(&h->ev[k]));
   CK(h, cudaDeviceSynchronize());
