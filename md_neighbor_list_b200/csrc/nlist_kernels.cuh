@@ -308,20 +308,35 @@ __global__ void __launch_bounds__(256) bin_kernel(const T* __restrict__ q, int32
   const int32_t M = gp.n_cells;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int32_t carry = 0, cmax = 0;
-  for (int32_t b0 = 0; b0 < M; b0 += 256 * 4) {
-    // 4 consecutive cells per thread
-    const int32_t c0 = b0 + threadIdx.x * 4;
-    int32_t v[4];
+  constexpr int CPT = 16;  // consecutive cells per thread: the default system's 3375 cells take ONE round
+  for (int32_t b0 = 0; b0 < M; b0 += 256 * CPT) {
+    const int32_t c0 = b0 + threadIdx.x * CPT;
+    int32_t v[CPT];
+    if (c0 + CPT <= M) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) v[k] = (c0 + k < M) ? __ldcg(cell_count + c0 + k) : 0;
-    const int32_t tsum = v[0] + v[1] + v[2] + v[3];
+      for (int k = 0; k < CPT; k += 4) {
+        const int4 t4 = __ldcg(reinterpret_cast<const int4*>(cell_count + c0 + k));
+        v[k] = t4.x;
+        v[k + 1] = t4.y;
+        v[k + 2] = t4.z;
+        v[k + 3] = t4.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < CPT; k++) v[k] = (c0 + k < M) ? __ldcg(cell_count + c0 + k) : 0;
+    }
+    int32_t tsum = 0, tm = 0;
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+      tsum += v[k];
+      tm = max(tm, v[k]);
+    }
     int32_t incl = tsum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int32_t o = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += o;
     }
-    int32_t tm = max(max(v[0], v[1]), max(v[2], v[3]));
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) tm = max(tm, __shfl_xor_sync(0xffffffffu, tm, d));
     __syncthreads();  // the previous round's wsum readers are done
@@ -337,10 +352,23 @@ __global__ void __launch_bounds__(256) bin_kernel(const T* __restrict__ q, int32
       cmax = max(cmax, wmax[k]);
     }
     int32_t run = carry + wpre + incl - tsum;
+    if (c0 + CPT <= M) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      if (c0 + k < M) cell_start[c0 + k] = run;
-      run += v[k];
+      for (int k = 0; k < CPT; k += 4) {
+        int4 o4;
+        o4.x = run;
+        o4.y = run + v[k];
+        o4.z = o4.y + v[k + 1];
+        o4.w = o4.z + v[k + 2];
+        run = o4.w + v[k + 3];
+        *reinterpret_cast<int4*>(cell_start + c0 + k) = o4;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < CPT; k++) {
+        if (c0 + k < M) cell_start[c0 + k] = run;
+        run += v[k];
+      }
     }
     carry += tot;
   }
