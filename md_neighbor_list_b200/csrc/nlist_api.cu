@@ -604,6 +604,19 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     }
     return NLB200_OK;
   };
+  // ... as a second branch of the graph beside an emission that writes the list only (called after the offsets scan)
+  auto fork_finalize = [&]() -> int {
+    if (!(n > 0 && !h->profile && !t_pdl && !h->sort_rows && h->mode != NLB200_FULL_ELL_TRANSPOSED && s != nullptr &&
+          s != cudaStreamLegacy && s != cudaStreamPerThread))
+      return NLB200_OK;
+    CK(h, cudaEventRecord(h->ev_fork, s));
+    CK(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    const int rc_fin = launch_finalize(h->side_stream, false);
+    if (rc_fin) return rc_fin;
+    CK(h, cudaEventRecord(h->ev_join, h->side_stream));
+    finalized_early = true;
+    return NLB200_OK;
+  };
   if (uses_rowmask(h)) {
     // --- default: row masks.  Search (every test once, verdict blocks transposed to row-major words, row lengths
     //     on the way) -> offsets -> emission. ---
@@ -739,14 +752,9 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
     // After the offsets scan nothing the status block reports can change any more on this path (the emission writes
     // the list only) and every kernel that reads the ghosts has run: finalize_kernel becomes a second branch of the
     // graph BESIDE the emission instead of a node behind it.
-    if (n > 0 && !h->profile && !t_pdl && !h->sort_rows && h->mode != NLB200_FULL_ELL_TRANSPOSED && s != nullptr &&
-        s != cudaStreamLegacy && s != cudaStreamPerThread) {
-      CK(h, cudaEventRecord(h->ev_fork, s));
-      CK(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-      const int rc_fin = launch_finalize(h->side_stream, false);
+    {
+      const int rc_fin = fork_finalize();
       if (rc_fin) return rc_fin;
-      CK(h, cudaEventRecord(h->ev_join, h->side_stream));
-      finalized_early = true;
     }
     if (n > 0) {
       EmitRunArgs em;
@@ -908,7 +916,13 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
                          h->status_dev, &h->status_dev->max_partners, (long long)h->cap_entries));
     }
     CK(h, stage(ST_EMIT));
+    if (!direct && gids == nullptr) {  // (the staged emission writes the list only; with a global-id map it still
+                                        //  reads ids the neighbours may overwrite once finalize_kernel has run)
+      const int rc_fin = fork_finalize();
+      if (rc_fin) return rc_fin;
+    }
     if (n > 0) CK(h, launch_emit(half_emit, false, direct, em, s));
+    if (finalized_early) CK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
   }
   if (h->sort_rows) CK(h, stage(ST_SORT_ROWS));
   if (h->sort_rows && n_owned > 0) {
