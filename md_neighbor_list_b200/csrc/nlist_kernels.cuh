@@ -657,6 +657,8 @@ __global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, 
     // sort key: the id the rows report — with a local -> global map the GLOBAL id, so that a cell's particles come
     // out in the order a single-GPU build of the whole system gives them, whatever order the ghosts arrived in
     const int32_t key = (valid && global_ids != nullptr) ? __ldg(global_ids + id) : id;
+    // the record is requested before the ranking loop: its (random, L2) latency overlaps the shuffles
+    const Vec3<T> p = load_pos<T, STRIDE>(q, valid ? id : 0);
     int32_t rank = 0;
     for (int32_t cb = 0; cb < cnt; cb += 32) {
       int32_t other = (cb + lane < cnt) ? __ldg(perm + beg + cb + lane) : 0x7fffffff;
@@ -665,7 +667,6 @@ __global__ void __launch_bounds__(128) cellsort_kernel(const T* __restrict__ q, 
       for (int t = 0; t < lim; t++) rank += (__shfl_sync(0xffffffffu, other, t) < key) ? 1 : 0;
     }
     if (valid) {
-      const Vec3<T> p = load_pos<T, STRIDE>(q, id);
       float4 r;
       r.x = ABS ? (float)p.x : (float)((double)p.x - ox);
       r.y = ABS ? (float)p.y : (float)((double)p.y - oy);
