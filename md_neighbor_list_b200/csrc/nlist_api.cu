@@ -57,6 +57,9 @@ struct nlb200_context {
   HaloPackArgs halo_pack{};              // nlb200_set_halo_pack: the exchange folded into the binning kernels
   bool halo_pack_on = false;
   int path = 0;                         // PATH_*: which search / emission pair the handle runs (pick_path)
+  bool half_needs_ids = false;          // a HALF handle has been given a global-id map: ids are not monotone in a cell
+  int64_t mic_alloc = 0;                // cell capacity the search buffers were last sized for
+  bool mic_alloc_bound = false;
   bool state_clean = false;             // the zero region is all zero (left so by the last build's finalize_kernel)
   int sm_count = 148;
   int64_t l2_bytes = 0;
@@ -325,6 +328,10 @@ cudaError_t set_runmask_attrs() {
   if ((e = cudaFuncSetAttribute(runmask_kernel<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(runmask_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(runmask_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(runmask_kernel<double, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(runmask_kernel<double, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(runmask_kernel<float, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(runmask_kernel<float, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(emitwin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(emitrun_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_EMIT_SMEM);
 }
@@ -365,18 +372,19 @@ cudaError_t launch_search(bool half, bool fill, bool exact, const SearchArgs<T>&
 
 
 // Which search / emission pair a handle runs.  NLB200_OPT_KERNEL_VARIANT:
-//   0 (default): PAIR MASKS (pairmask_kernel, rowcount_kernel, emit_kernel) while the per-particle mask planes stay
-//                small — their size is 108 * ceil(max_in_cell / 32) bytes per particle — and ROW MASKS
-//                (rowmask4_kernel, emit3_kernel: one bit per test, a block per cell from a cursor) once a cell may
-//                hold more than PAIRMASK_MAX_CELL particles (clustered inputs): nlb200_reserve_cell_capacity switches.
-//                On the density-1.0 default system the two pairs are within 3 % of each other (157.7 vs 161.8 us).
+//   0 (default): RUN MASKS (runmask_kernel + emitrun_kernel / emitwin_kernel, nlist_runmask.cuh) — FULL lists, and HALF
+//                lists whose ids ascend with the slot inside a cell (no global-id map: the id cut is a per-cell suffix).
+//                Emission: emitrun_kernel (ids gathered from global memory) below EMITWIN_MIN_PARTICLES particles,
+//                emitwin_kernel (ids through a shared-memory window) from there on; 9 / 10 force the one / the other.
+//                HALF lists WITH a global-id map (multi-GPU): PAIR MASKS (pairmask_kernel, rowcount_kernel, emit_kernel
+//                with its id filter), or ROW MASKS once the pair masks exceed the L2.
+//                Any mode with a cell of more than PAIRMASK_MAX_CELL particles (clustered inputs): ROW MASKS
+//                (rowmask4_kernel, emit3_kernel: one bit per test, a block per cell from a cursor);
+//                nlb200_reserve_cell_capacity switches.
 //   1, or NLB200_OPT_EXACT_ONLY: search_kernel twice (count, fill): every test in the input precision if asked
 //   2, 3, 4, 7, 100..:           pair masks and their ablations
 //   5: row masks with the CTA-per-cell search (rowmask_kernel)      6, 20..39: row masks (rowmask4_kernel)
-//   8, or the default for FULL lists: RUN MASKS (runmask_kernel, emitwin_kernel; nlist_runmask.cuh)
-//                emission: emitrun_kernel (ids gathered from global memory) below EMITWIN_MIN_PARTICLES particles,
-//                emitwin_kernel (ids through a shared-memory window) from there on;  9 / 10 force the one / the other
-//   200..299: run masks with (variant - 200) units per cell (tuning)
+//   8: run masks (= default)     200..299: run masks with (variant - 200) units per cell (tuning)
 enum { PATH_V1 = 1, PATH_PAIRMASK = 2, PATH_ROWMASK = 3, PATH_RUNMASK = 4 };
 constexpr int64_t PAIRMASK_MAX_CELL = 256;
 constexpr int32_t EMITWIN_MIN_PARTICLES = 1 << 20;
@@ -386,8 +394,11 @@ int pick_path(const nlb200_context* h, int64_t max_in_cell) {
   const bool rn_tuning = h->variant == 9 || h->variant == 10 || (h->variant >= 200 && h->variant < 300);
   if (h->variant != 0 && h->variant != 8 && !rn_tuning) return PATH_PAIRMASK;
   if (max_in_cell > PAIRMASK_MAX_CELL) return PATH_ROWMASK;
-  if (h->mode != NLB200_HALF_CSR) return PATH_RUNMASK;  // 36 bytes x words-per-run per particle, dense
-  if (h->variant == 8) return PATH_PAIRMASK;
+  // HALF lists take the run masks too: the id cut is a per-cell suffix (ids ascend with the slot inside a cell) — until
+  // the handle is given a global-id map (multi-GPU), whose ids are not monotone: then the pair / row masks with the
+  // emission's id filter (nlb200_build_subset switches the handle over, once)
+  if (h->mode != NLB200_HALF_CSR || !h->half_needs_ids) return PATH_RUNMASK;  // 36 bytes x words-per-run per particle
+  if (h->variant == 8 || rn_tuning) return PATH_PAIRMASK;
   // Large systems: once the pair masks (324 bytes per particle at 3 words per stencil cell) no longer fit the L2 they
   // make a round trip through HBM; the row masks hold one bit per evaluated test (~120 bytes per particle) and need no
   // popcount pass over them.  Same build time within 1-2 % at 2 M and 16.8 M uniform particles
@@ -718,7 +729,13 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
       rn.st = h->status_dev;
       const size_t rn_smem = rn_warp_bytes(h->mask_wr) * (RN_THREADS / 32);
       int per_sm = 0;
-      CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, runmask_kernel<T, STRIDE>, RN_THREADS, rn_smem));
+      if (half && gids != nullptr)
+        return fail(h, NLB200_ERR_INVALID, "HALF run masks cut rows by slot order: no global-id map (use the pair masks)");
+      if (half)
+        CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, runmask_kernel<T, STRIDE, true>, RN_THREADS,
+                                                            rn_smem));
+      else
+        CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, runmask_kernel<T, STRIDE>, RN_THREADS, rn_smem));
       if (per_sm < 1) return fail(h, NLB200_ERR_CUDA, "run-mask kernel does not fit an SM (%zu bytes of shared memory)", rn_smem);
       int64_t grid = (int64_t)per_sm * h->sm_count;
       const int64_t resident = grid * (RN_THREADS / 32);
@@ -739,7 +756,10 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
       rn.d_my = make_fastdiv((uint32_t)gp.mesh[1]);
       const int64_t need = (M * parts + RN_THREADS / 32 - 1) / (RN_THREADS / 32);
       if (grid > need) grid = need;
-      CK(h, launch_chain(runmask_kernel<T, STRIDE>, dim3((unsigned)grid), dim3(RN_THREADS), rn_smem, s, rn));
+      if (half)
+        CK(h, launch_chain(runmask_kernel<T, STRIDE, true>, dim3((unsigned)grid), dim3(RN_THREADS), rn_smem, s, rn));
+      else
+        CK(h, launch_chain(runmask_kernel<T, STRIDE>, dim3((unsigned)grid), dim3(RN_THREADS), rn_smem, s, rn));
     }
     CK(h, stage(ST_SCAN_COUNTS));
     {
@@ -978,6 +998,7 @@ int alloc_mask(nlb200_context* h, int64_t max_in_cell) {
   if (h->mask) cudaFree(h->mask);
   h->mask = fresh;
   h->mask_wi = (int32_t)wi;
+  h->mask_wr = 0;
   h->mask_ncap = ncap;
   return NLB200_OK;
 }
@@ -1032,6 +1053,8 @@ int alloc_rmask(nlb200_context* h, int64_t words) {
 // Buffers of the handle's search path for cells of up to `mic` particles.
 // mic_is_bound: mic was given by the caller or seen in a build (else it is initialize's density estimate).
 int alloc_search_buffers(nlb200_context* h, int64_t mic, bool mic_is_bound = false) {
+  h->mic_alloc = mic;
+  h->mic_alloc_bound = mic_is_bound;
   const int64_t n = h->max_n > 0 ? h->max_n : 1;
   const int64_t M = h->n_cells;
   if (uses_rowmask(h)) {
@@ -1340,6 +1363,19 @@ int nlb200_build_subset(nlb200_handle h, const void* q_dev, int64_t n_total, int
     return fail(h, NLB200_ERR_INVALID, "position pointer must be %zu-byte aligned", align);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int rc = NLB200_OK;
+  if (h->mode == NLB200_HALF_CSR && global_ids_dev != nullptr && !h->half_needs_ids) {
+    // first build of a HALF handle with a local -> global id map: the run masks' id cut assumes ids that ascend with
+    // the slot inside a cell; move the handle to the masks whose emission filters by id (once; buffers re-sized)
+    h->half_needs_ids = true;
+    const int want = pick_path(h, h->mic_alloc > 0 ? h->mic_alloc : 1);
+    if (want != h->path) {
+      CK(h, settle_before_realloc(h));
+      h->path = want;
+      h->rmask_need = 0;
+      rc = alloc_search_buffers(h, h->mic_alloc > 0 ? h->mic_alloc : estimate_max_in_cell(h, h->max_n), h->mic_alloc_bound);
+      if (rc) return rc;
+    }
+  }
   if (h->mode == NLB200_FULL_ELL_TRANSPOSED && n_owned != h->ell_last_n) {
     // the view's row stride is the particle count (list[k*N + i], kernel_impl.cuh:30): a new N re-lays the matrix
     // out, so start again from the reference's initial state (all -1, neighlist_gpu.hpp:271-274)

@@ -73,7 +73,7 @@ struct RunMaskArgs {
 
 // One chunk of RJ x 32 candidates against every row of the run.  `staged` tells whether the (single) row round of
 // the run already sits in shared memory (runs of more than RN_SW words are re-staged round by round).
-template <typename T, int STRIDE, int RJ>
+template <typename T, int STRIDE, int RJ, bool HALF>
 __device__ __forceinline__ void rn_chunk(const RunMaskArgs<T>& a, float4* si, const int4* t_col, const float2* t_tr,
                                          const int lane, const int32_t c0, const int32_t ncand, const int32_t rs,
                                          const int32_t n_r, const int32_t b1, const int32_t b2, const float tx0,
@@ -143,6 +143,40 @@ __device__ __forceinline__ void rn_chunk(const RunMaskArgs<T>& a, float4* si, co
 #pragma unroll
     for (int k = 0; k < RJ; k++) row_needed = row_needed || oj[k] >= 0;
     if (!__any_sync(0xffffffffu, row_needed)) return;
+  }
+  // HALF lists (row j keeps the partners with a larger id): the ids of a cell ascend with the slot, so inside each of
+  // the run's <= 3 cells the kept rows are a SUFFIX.  cut[k][c] = run-relative index of the first kept row of cell c for
+  // candidate k: cell start + #{ids of the cell <= id_j}, found by a branch-free binary search (uniform step count, the
+  // 3 * RJ searches of a lane interleaved); every word is then cut with at most three range masks — no per-test cost.
+  int32_t cut[RJ][3];
+  int32_t cs_[4];  // run-relative starts of the three cells and the end of the run
+  if (HALF) {
+    cs_[0] = 0;
+    cs_[1] = min(b1 == 0x7fffffff ? n_r : b1 - rs, n_r);
+    cs_[2] = min(b2 == 0x7fffffff ? n_r : b2 - rs, n_r);
+    cs_[3] = n_r;
+    const int32_t maxlen = max(cs_[1], max(cs_[2] - cs_[1], n_r - cs_[2]));
+    int32_t pos[RJ][3];
+#pragma unroll
+    for (int k = 0; k < RJ; k++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) pos[k][c] = 0;
+    const int32_t* ids = a.sorted_ids + rs;
+    for (int32_t bit = 1 << (31 - __clz(max(maxlen, 1))); bit > 0; bit >>= 1) {
+#pragma unroll
+      for (int k = 0; k < RJ; k++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const int32_t t = pos[k][c] + bit;
+          const bool in = t <= cs_[c + 1] - cs_[c];
+          const int32_t v = in ? __ldg(ids + cs_[c] + t - 1) : 0x7fffffff;
+          if (v <= idj[k]) pos[k][c] = t;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RJ; k++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) cut[k][c] = cs_[c] + pos[k][c];
   }
   f32x2 X[RJ / 2], Y[RJ / 2], Z[RJ / 2], W[RJ / 2];
 #pragma unroll
@@ -239,9 +273,21 @@ __device__ __forceinline__ void rn_chunk(const RunMaskArgs<T>& a, float4* si, co
           }
         }
       }
+      if (HALF) {
+        // drop the rows [cell start, cut) of every cell that meets this word (the own bit goes with them: id == id)
+        const int32_t wb = w * 32;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          if (cs_[c] >= wb + 32 || cs_[c + 1] <= wb) continue;  // warp-uniform
+          const uint32_t from = __funnelshift_rc(0xffffffffu, 0u, (uint32_t)max(cs_[c] - wb, 0));
+#pragma unroll
+          for (int k = 0; k < RJ; k++)
+            hits[k] &= ~(from & ~__funnelshift_rc(0xffffffffu, 0u, (uint32_t)max(cut[k][c] - wb, 0)));
+        }
+      }
 #pragma unroll
       for (int k = 0; k < RJ; k++) {
-        if (selfw[k] == w) hits[k] &= ~selfm[k];  // FULL rows hold j != i (kernel_impl.cuh:29)
+        if (!HALF && selfw[k] == w) hits[k] &= ~selfm[k];  // FULL rows hold j != i (kernel_impl.cuh:29)
         pc[k] += __popc(hits[k]);
       }
       if (a.fits32) {
@@ -262,7 +308,7 @@ __device__ __forceinline__ void rn_chunk(const RunMaskArgs<T>& a, float4* si, co
     if (oj[k] >= 0 && pc[k] != 0) atomicAdd(a.counts + idj[k], pc[k]);
 }
 
-template <typename T, int STRIDE>
+template <typename T, int STRIDE, bool HALF = false>
 __global__ void __launch_bounds__(RN_THREADS, NLB_RN_MINB) runmask_kernel(RunMaskArgs<T> a) {
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -343,13 +389,13 @@ __global__ void __launch_bounds__(RN_THREADS, NLB_RN_MINB) runmask_kernel(RunMas
         const int32_t rem = ncand - c0;
         if (RN_RJ >= 4 && rem <= RN_CH / 2) {
           if (RN_RJ >= 8 && rem <= RN_CH / 4)
-            rn_chunk<T, STRIDE, (RN_RJ >= 8 ? RN_RJ / 4 : 2)>(a, si, t_col, t_tr, lane, c0, ncand, rs, n_r, b1, b2, tx0,
+            rn_chunk<T, STRIDE, (RN_RJ >= 8 ? RN_RJ / 4 : 2), HALF>(a, si, t_col, t_tr, lane, c0, ncand, rs, n_r, b1, b2, tx0,
                                                               staged, band_local);
           else
-            rn_chunk<T, STRIDE, (RN_RJ >= 4 ? RN_RJ / 2 : 2)>(a, si, t_col, t_tr, lane, c0, ncand, rs, n_r, b1, b2, tx0,
+            rn_chunk<T, STRIDE, (RN_RJ >= 4 ? RN_RJ / 2 : 2), HALF>(a, si, t_col, t_tr, lane, c0, ncand, rs, n_r, b1, b2, tx0,
                                                               staged, band_local);
         } else {
-          rn_chunk<T, STRIDE, RN_RJ>(a, si, t_col, t_tr, lane, c0, ncand, rs, n_r, b1, b2, tx0, staged, band_local);
+          rn_chunk<T, STRIDE, RN_RJ, HALF>(a, si, t_col, t_tr, lane, c0, ncand, rs, n_r, b1, b2, tx0, staged, band_local);
         }
       }
     }

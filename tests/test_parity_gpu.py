@@ -860,6 +860,64 @@ def test_run_mask_path_on_every_input_class(cuda, oracle, variant):
     nl.close()
 
 
+def test_half_lists_on_run_masks(cuda, oracle):
+    """HALF lists take the run masks too (runmask_kernel<HALF>): row j keeps the partners with a larger id, and because
+    the ids of a cell ascend with the slot the kept rows of each of a run's <= 3 cells are a suffix — found by a
+    branch-free binary search per (candidate, cell), applied as range masks per word.  Against the oracle and, entry
+    by entry, against the pair-mask path (variant 2) on: both default systems, 3-cell axes with duplicates, a sparse
+    box, ~100 particles per cell (multi-word cells, two staged row rounds), FP32 positions, random ids; then a handle
+    that is given a global-id map after a plain build (ids no longer monotone in a cell: it moves to the pair masks)."""
+    from md_neighbor_list_b200 import VerletListB200, workloads
+    torch = cuda
+    rng = np.random.default_rng(3)
+    cases = [(workloads.fcc(d, 50.0), 3.3, (50.0,) * 3, "f64") for d in (0.5, 1.0)]
+    q = np.zeros((5000, 4))
+    q[:, :3] = rng.random((5000, 3)) * np.array((13.0, 29.5, 10.1))
+    q[150:170, :3] = q[170:190, :3]
+    cases.append((q, 3.3, (13.0, 29.5, 10.1), "f64"))
+    q = np.zeros((300, 4))
+    q[:, :3] = rng.random((300, 3)) * 60.0
+    cases.append((q, 3.3, (60.0,) * 3, "f64"))
+    q = np.zeros((21600, 4))
+    q[:, :3] = rng.random((21600, 3)) * 20.0
+    cases.append((q, 3.3, (20.0,) * 3, "f64"))
+    cases.append((workloads.fcc(1.0, 30.0).astype(np.float32), 3.3, (30.0,) * 3, "f32"))
+    q = np.zeros((200000, 4))
+    q[:, :3] = rng.random((200000, 3)) * 58.0
+    cases.append((q[rng.permutation(200000)], 3.3, (58.0,) * 3, "f64"))
+    for q, sl, box, dt in cases:
+        got = gpu_build(cuda, q, sl, box, "half_csr", dtype=dt)
+        assert_matches(oracle, got, oracle.build_half(q, sl, box))
+        pm = gpu_build(cuda, q, sl, box, "half_csr", dtype=dt, kernel_variant=2)
+        assert np.array_equal(pm["list"], got["list"]) and np.array_equal(pm["off"], got["off"])
+    # the same handle: a plain HALF build (run masks), then an owned subset with a global-id map (pair masks), then plain
+    L = 24.0
+    q = workloads.fcc(1.0, L)
+    n = q.shape[0]
+    perm = rng.permutation(n).astype(np.int32)
+    n_owned = n // 3
+    ql = np.ascontiguousarray(q[perm])
+    ref = oracle.build_half(q, 3.3, (L, L, L)).sorted_rows()
+    nl = VerletListB200(3.3, L, L, L, mode="half_csr")
+    nl.initialize(n)
+    for with_map in (False, True, False):
+        if with_map:
+            nl.build(torch.from_numpy(ql).cuda(), n_owned=n_owned, global_ids=torch.from_numpy(perm).cuda())
+        else:
+            nl.build(torch.from_numpy(q).cuda())
+        nl.synchronize()
+        off = nl.offsets().cpu().numpy()
+        lst = sort_rows(oracle, nl.partners().cpu().numpy(), off)
+        if with_map:
+            assert np.array_equal(nl.number_of_partners().cpu().numpy(), ref.number_of_partners[perm[:n_owned]])
+            for li in range(0, n_owned, 17):
+                g = perm[li]
+                assert np.array_equal(lst[off[li]:off[li + 1]], ref.partners[ref.offsets[g]:ref.offsets[g + 1]])
+        else:
+            assert np.array_equal(off, ref.offsets) and np.array_equal(lst, ref.partners)
+    nl.close()
+
+
 def test_programmatic_dependent_launch_gives_the_same_list(cuda, oracle, monkeypatch):
     """NLB200_OPT_PDL (environment override NLB200_PDL=1): the kernels of a build chained by programmatic dependent
     launch instead of plain stream order — graph replay and plain launches — must not change a bit of the result."""
