@@ -57,7 +57,6 @@ struct nlb200_context {
   HaloPackArgs halo_pack{};              // nlb200_set_halo_pack: the exchange folded into the binning kernels
   bool halo_pack_on = false;
   int path = 0;                         // PATH_*: which search / emission pair the handle runs (pick_path)
-  bool half_needs_ids = false;          // a HALF handle has been given a global-id map: ids are not monotone in a cell
   int64_t mic_alloc = 0;                // cell capacity the search buffers were last sized for
   bool mic_alloc_bound = false;
   bool state_clean = false;             // the zero region is all zero (left so by the last build's finalize_kernel)
@@ -372,12 +371,10 @@ cudaError_t launch_search(bool half, bool fill, bool exact, const SearchArgs<T>&
 
 
 // Which search / emission pair a handle runs.  NLB200_OPT_KERNEL_VARIANT:
-//   0 (default): RUN MASKS (runmask_kernel + emitrun_kernel / emitwin_kernel, nlist_runmask.cuh) — FULL lists, and HALF
-//                lists whose ids ascend with the slot inside a cell (no global-id map: the id cut is a per-cell suffix).
+//   0 (default): RUN MASKS (runmask_kernel + emitrun_kernel / emitwin_kernel, nlist_runmask.cuh) — FULL and HALF lists.
 //                Emission: emitrun_kernel (ids gathered from global memory) below EMITWIN_MIN_PARTICLES particles,
 //                emitwin_kernel (ids through a shared-memory window) from there on; 9 / 10 force the one / the other.
-//                HALF lists WITH a global-id map (multi-GPU): PAIR MASKS (pairmask_kernel, rowcount_kernel, emit_kernel
-//                with its id filter), or ROW MASKS once the pair masks exceed the L2.
+//                (a cell is ordered by the id its rows report — local, or global with a map — so the HALF cut is a suffix)
 //                Any mode with a cell of more than PAIRMASK_MAX_CELL particles (clustered inputs): ROW MASKS
 //                (rowmask4_kernel, emit3_kernel: one bit per test, a block per cell from a cursor);
 //                nlb200_reserve_cell_capacity switches.
@@ -394,18 +391,9 @@ int pick_path(const nlb200_context* h, int64_t max_in_cell) {
   const bool rn_tuning = h->variant == 9 || h->variant == 10 || (h->variant >= 200 && h->variant < 300);
   if (h->variant != 0 && h->variant != 8 && !rn_tuning) return PATH_PAIRMASK;
   if (max_in_cell > PAIRMASK_MAX_CELL) return PATH_ROWMASK;
-  // HALF lists take the run masks too: the id cut is a per-cell suffix (ids ascend with the slot inside a cell) — until
-  // the handle is given a global-id map (multi-GPU), whose ids are not monotone: then the pair / row masks with the
-  // emission's id filter (nlb200_build_subset switches the handle over, once)
-  if (h->mode != NLB200_HALF_CSR || !h->half_needs_ids) return PATH_RUNMASK;  // 36 bytes x words-per-run per particle
-  if (h->variant == 8 || rn_tuning) return PATH_PAIRMASK;
-  // Large systems: once the pair masks (324 bytes per particle at 3 words per stencil cell) no longer fit the L2 they
-  // make a round trip through HBM; the row masks hold one bit per evaluated test (~120 bytes per particle) and need no
-  // popcount pass over them.  Same build time within 1-2 % at 2 M and 16.8 M uniform particles
-  // (profiles/r02_large_systems.md), 40 % less mask traffic.
-  const int64_t wi = (std::max<int64_t>(max_in_cell, 1) + 31) / 32;
-  if (h->l2_bytes > 0 && 108 * wi * h->max_n > h->l2_bytes) return PATH_ROWMASK;
-  return PATH_PAIRMASK;
+  // HALF lists take the run masks too: the id cut is a per-cell suffix (cellsort_kernel orders a cell by the id its
+  // rows report — the local id, or the global id of a local -> global map)
+  return PATH_RUNMASK;  // 36 bytes x words-per-run per particle, dense
 }
 bool uses_v1(const nlb200_context* h) { return h->path == PATH_V1; }
 bool uses_rowmask(const nlb200_context* h) { return h->path == PATH_ROWMASK; }
@@ -718,6 +706,8 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
       rn.cell_start = h->cell_start;
       rn.rec = h->rec;
       rn.sorted_ids = h->sorted_ids;
+      rn.cut_ids = gids != nullptr ? h->slot_gid : h->sorted_ids;
+      rn.cut_by_slot_table = gids != nullptr ? 1 : 0;
       rn.n_owned = (int32_t)n_owned;
       rn.mask = h->mask;
       rn.n_cap = h->mask_ncap;
@@ -729,8 +719,6 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
       rn.st = h->status_dev;
       const size_t rn_smem = rn_warp_bytes(h->mask_wr) * (RN_THREADS / 32);
       int per_sm = 0;
-      if (half && gids != nullptr)
-        return fail(h, NLB200_ERR_INVALID, "HALF run masks cut rows by slot order: no global-id map (use the pair masks)");
       if (half)
         CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, runmask_kernel<T, STRIDE, true>, RN_THREADS,
                                                             rn_smem));
@@ -1363,19 +1351,6 @@ int nlb200_build_subset(nlb200_handle h, const void* q_dev, int64_t n_total, int
     return fail(h, NLB200_ERR_INVALID, "position pointer must be %zu-byte aligned", align);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int rc = NLB200_OK;
-  if (h->mode == NLB200_HALF_CSR && global_ids_dev != nullptr && !h->half_needs_ids) {
-    // first build of a HALF handle with a local -> global id map: the run masks' id cut assumes ids that ascend with
-    // the slot inside a cell; move the handle to the masks whose emission filters by id (once; buffers re-sized)
-    h->half_needs_ids = true;
-    const int want = pick_path(h, h->mic_alloc > 0 ? h->mic_alloc : 1);
-    if (want != h->path) {
-      CK(h, settle_before_realloc(h));
-      h->path = want;
-      h->rmask_need = 0;
-      rc = alloc_search_buffers(h, h->mic_alloc > 0 ? h->mic_alloc : estimate_max_in_cell(h, h->max_n), h->mic_alloc_bound);
-      if (rc) return rc;
-    }
-  }
   if (h->mode == NLB200_FULL_ELL_TRANSPOSED && n_owned != h->ell_last_n) {
     // the view's row stride is the particle count (list[k*N + i], kernel_impl.cuh:30): a new N re-lays the matrix
     // out, so start again from the reference's initial state (all -1, neighlist_gpu.hpp:271-274)

@@ -57,6 +57,8 @@ struct RunMaskArgs {
   const int32_t* cell_start;
   const float4* rec;  // cell-sorted records relative to the particle's own cell corner, .w = local id
   const int32_t* sorted_ids;
+  const int32_t* cut_ids;  // HALF: the id per slot the rows are cut by — sorted_ids, or the global id per slot
+  int32_t cut_by_slot_table;  // HALF: the candidate's key is cut_ids[its slot] (global ids) instead of its local id
   int32_t n_owned;
   uint32_t* mask;  // [9][wr][n_cap]
   long long n_cap;
@@ -144,7 +146,7 @@ __device__ __forceinline__ void rn_chunk(const RunMaskArgs<T>& a, float4* si, co
     for (int k = 0; k < RJ; k++) row_needed = row_needed || oj[k] >= 0;
     if (!__any_sync(0xffffffffu, row_needed)) return;
   }
-  // HALF lists (row j keeps the partners with a larger id): the ids of a cell ascend with the slot, so inside each of
+  // HALF lists (row j keeps the partners with a larger id — the id its rows report): the ids of a cell ascend with the slot, so inside each of
   // the run's <= 3 cells the kept rows are a SUFFIX.  cut[k][c] = run-relative index of the first kept row of cell c for
   // candidate k: cell start + #{ids of the cell <= id_j}, found by a branch-free binary search (uniform step count, the
   // 3 * RJ searches of a lane interleaved); every word is then cut with at most three range masks — no per-test cost.
@@ -161,7 +163,12 @@ __device__ __forceinline__ void rn_chunk(const RunMaskArgs<T>& a, float4* si, co
     for (int k = 0; k < RJ; k++)
 #pragma unroll
       for (int c = 0; c < 3; c++) pos[k][c] = 0;
-    const int32_t* ids = a.sorted_ids + rs;
+    // (a local -> global id map: cellsort_kernel orders a cell by GLOBAL id, so the suffix property holds for the
+    //  global ids the rows report; key and table are then the global ids per slot)
+    const int32_t* ids = a.cut_ids + rs;
+    int32_t key[RJ];
+#pragma unroll
+    for (int k = 0; k < RJ; k++) key[k] = a.cut_by_slot_table ? __ldg(a.cut_ids + sj[k]) : idj[k];
     for (int32_t bit = 1 << (31 - __clz(max(maxlen, 1))); bit > 0; bit >>= 1) {
 #pragma unroll
       for (int k = 0; k < RJ; k++)
@@ -170,7 +177,7 @@ __device__ __forceinline__ void rn_chunk(const RunMaskArgs<T>& a, float4* si, co
           const int32_t t = pos[k][c] + bit;
           const bool in = t <= cs_[c + 1] - cs_[c];
           const int32_t v = in ? __ldg(ids + cs_[c] + t - 1) : 0x7fffffff;
-          if (v <= idj[k]) pos[k][c] = t;
+          if (v <= key[k]) pos[k][c] = t;
         }
     }
 #pragma unroll

@@ -866,7 +866,8 @@ def test_half_lists_on_run_masks(cuda, oracle):
     branch-free binary search per (candidate, cell), applied as range masks per word.  Against the oracle and, entry
     by entry, against the pair-mask path (variant 2) on: both default systems, 3-cell axes with duplicates, a sparse
     box, ~100 particles per cell (multi-word cells, two staged row rounds), FP32 positions, random ids; then a handle
-    that is given a global-id map after a plain build (ids no longer monotone in a cell: it moves to the pair masks)."""
+    that is given a local -> global id map between plain builds (a cell is then ordered by GLOBAL id and the rows are
+    cut by the global id per slot: the rows a slab rank builds in HALF mode)."""
     from md_neighbor_list_b200 import VerletListB200, workloads
     torch = cuda
     rng = np.random.default_rng(3)
@@ -890,7 +891,7 @@ def test_half_lists_on_run_masks(cuda, oracle):
         assert_matches(oracle, got, oracle.build_half(q, sl, box))
         pm = gpu_build(cuda, q, sl, box, "half_csr", dtype=dt, kernel_variant=2)
         assert np.array_equal(pm["list"], got["list"]) and np.array_equal(pm["off"], got["off"])
-    # the same handle: a plain HALF build (run masks), then an owned subset with a global-id map (pair masks), then plain
+    # the same handle: a plain HALF build, then an owned subset with a global-id map, then plain again
     L = 24.0
     q = workloads.fcc(1.0, L)
     n = q.shape[0]
