@@ -1,25 +1,28 @@
 // nlist_kernels.cuh — hand-written sm_100a kernels of the Verlet-list build.
 //
-// Pipeline of one build (all on one stream, replayed as a CUDA graph):
-//   zero  -> bin_kernel        cell index + histogram            (reference: make_mesh, neighlist_gpu.hpp:26-41;
-//                                                                 MakeMeshidOfPtcl, neighlist_cpu.hpp:134-144)
-//         -> scan_kernel       exclusive scan of the histogram   (thrust::inclusive_scan, neighlist_gpu.hpp:173-175;
-//                                                                 MakeNextDest, neighlist_cpu.hpp:146-152)
-//         -> scatter_kernel    counting-sort scatter of ids      (thrust::sort_by_key, neighlist_gpu.hpp:190-199;
+// Pipeline of one build (one stream, replayed as a CUDA graph; the per-build state is left zeroed by the previous build):
+//   bin_kernel        cell index + histogram; its last CTA scans the histogram into cell_start (scan_kernel on grids
+//                     of more than 8192 cells); a slab rank's launch also SENDS its face records to the neighbours
+//                                                                (reference: make_mesh, neighlist_gpu.hpp:26-41;
+//                                                                 MakeMeshidOfPtcl / MakeNextDest, neighlist_cpu.hpp:134-152;
+//                                                                 thrust::inclusive_scan, neighlist_gpu.hpp:173-175)
+//   -> scatter_kernel    counting-sort scatter of ids            (thrust::sort_by_key, neighlist_gpu.hpp:190-199;
 //                                                                 neighlist_cpu.hpp:154-160)
-//         -> cellsort_kernel   ids ascending inside a cell + cell-sorted FP32 position records
+//   -> cellsort_kernel   ids ascending inside a cell + cell-sorted FP32 position records
 //                                                                (the SortPtclData / CopyGather the reference stubbed
 //                                                                 out: neighlist_cpu.hpp:176-180, neighlist_gpu.hpp:144-151)
-//         -> pairmask_kernel   pair search: every ordered pair tested once, verdicts kept as bit masks
-//                                                                (kernel_impl.cuh:3-436, neighlist_cpu.hpp:239-359)
-//         -> rowcount_kernel   FULL: row length = popcount  /  emit_kernel<COUNT>  HALF: ids needed to count
-//         -> scan_kernel       counts -> CSR offsets             (MakeNeighListForEachPtcl, neighlist_cpu.hpp:361-367)
-//         -> emit_kernel       bits -> partner ids, rows written with 16-byte stores (neighlist_cpu.hpp:369-372;
-//                                                                 replaces the row-major buffer + cublasSgeam
-//                                                                 transpose, kernel_impl.cuh:217-239)
-//         -> [sort_rows_kernel] [ell_kernel]
-//   search_kernel (one CTA per cell, test evaluated in a count and a fill pass) is the round-0 search, kept as
-//   NLB200_OPT_KERNEL_VARIANT = 1 and for NLB200_OPT_EXACT_ONLY; emit_direct_kernel is an ablation (variant 3).
+//   -> runmask_kernel    (nlist_runmask.cuh) pair search: every ordered pair tested once, verdicts kept as bit masks,
+//                        row lengths by RED                      (kernel_impl.cuh:3-436, neighlist_cpu.hpp:239-359)
+//   -> scan_kernel       row lengths -> CSR offsets              (MakeNeighListForEachPtcl, neighlist_cpu.hpp:361-367)
+//   -> emitrun_kernel / emitwin_kernel   bits -> partner ids, rows written with 32-byte stores
+//                                                                (neighlist_cpu.hpp:369-372; replaces the row-major
+//                                                                 buffer + cublasSgeam transpose, kernel_impl.cuh:217-239)
+//      || finalize_kernel   status block to mapped host memory, per-build state re-zeroed (a second graph branch)
+//   -> [sort_rows_kernel] [ell_kernel]
+//   Other searches in this file: pairmask_kernel + rowcount_kernel + emit_kernel (round 1's pair masks, kept as
+//   NLB200_OPT_KERNEL_VARIANT = 2: the independent implementation the tests compare the run masks with);
+//   search_kernel (one CTA per cell, test evaluated in a count and a fill pass: variant 1 and NLB200_OPT_EXACT_ONLY);
+//   emit_direct_kernel only with -DNLB_ABLATIONS.  Crowded cells: nlist_rowmask.cuh.
 //
 // Not a port: the reference searches with one thread/warp per particle gathering unsorted positions by id and writes
 // an ELL matrix.  Here positions are physically cell-sorted as 16-byte FP32 records relative to their cell corner; the

@@ -1,4 +1,4 @@
-// nlist_runmask.cuh — "run masks": the search + emission pair of FULL lists (round 2).
+// nlist_runmask.cuh — "run masks": the search + emission pair of FULL and HALF lists (round 2).
 //
 // What changed against the pair masks (nlist_kernels.cuh) and why.  There the unit of work is (cell A, 256 candidates
 // of A's 27-cell stencil): the ~35 particles i of A are the BITS of a word, the candidates j sit on the lanes, and by
@@ -21,6 +21,9 @@
 //     staging, candidate look-ups) is amortised over three times the main-loop work;
 //   * the row's own bit is cleared where it is produced, and the row length leaves the search kernel by one
 //     RED.ADD per (row, run): the popcount pass (15 us on the default system) is gone.
+//   * HALF lists (row j keeps the larger ids): a cell is ordered by the id its rows report, so the kept rows of each
+//     of a run's <= 3 cells are a suffix — one binary search per (candidate, cell), range masks per word, no per-test
+//     cost (runmask_kernel<HALF>).
 // The test itself is round 1's: dot form d = xi.xj - |xj|^2/2 - (|xi|^2 - SL^2)/2 in FP32 with packed FFMA2/FADD2,
 // sign bit funnel-shifted into the word, min|d| tracked, exact input-precision re-test inside the band E.
 #pragma once
