@@ -570,12 +570,19 @@ int enqueue_build(nlb200_context* h, const T* q, int64_t n_total, int64_t n_owne
       CK(h, launch_chain(cellsort_kernel<T, STRIDE, true>, dim3((unsigned)cs_blocks), dim3(128), 0, s, q, gp,
                          (const int32_t*)h->cell_start, (const int32_t*)h->perm, h->sorted_ids, h->rec, h->slot_cell,
                          gids, h->slot_gid, h->variant == 5 ? (CellRec*)nullptr : h->cellrec,
-                         (unsigned long long)h->rmask_cap, h->counts, (int32_t)n_owned, h->status_dev, cs_batch));
+                         (unsigned long long)h->rmask_cap, h->counts, (int32_t)n_owned, h->status_dev, cs_batch,
+                         (int32_t)CS_BIG));
     else
       CK(h, launch_chain(cellsort_kernel<T, STRIDE, false>, dim3((unsigned)cs_blocks), dim3(128), 0, s, q, gp,
                          (const int32_t*)h->cell_start, (const int32_t*)h->perm, h->sorted_ids, h->rec, h->slot_cell,
                          gids, h->slot_gid, (CellRec*)nullptr, 0ull, uses_runmask(h) ? h->counts : (int32_t*)nullptr,
-                         (int32_t)n_owned, h->status_dev, 1));
+                         (int32_t)n_owned, h->status_dev, 1, 0));
+    if (uses_rowmask(h))
+      // the crowded cells' particles: one warp per 32 slots instead of one warp per cell (see cellsort_big_kernel)
+      CK(h, launch_chain(cellsort_big_kernel<T, STRIDE, true>, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, s, q, gp,
+                         (const int32_t*)h->cell_start, (const int2*)h->cell_rank, (const int32_t*)h->perm,
+                         h->sorted_ids, h->rec, h->slot_cell, gids, h->slot_gid, h->counts, (int32_t)n_owned,
+                         (int32_t)CS_BIG));
   }
   const bool half = h->mode == NLB200_HALF_CSR;
   const bool use_v1 = uses_v1(h);
