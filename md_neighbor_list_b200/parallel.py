@@ -209,6 +209,39 @@ class SlabDecomposition:
         self._last = (self._qall, self._gall, n)
         return self._last
 
+    def refresh(self, nl, q_owned: torch.Tensor, stream=None):
+        """Incremental halo refresh over the send/recv transport: between two builds, the records
+        the last exchange sent — the same particles, in the same order, found again through the global ids that went
+        with them (the owned global ids must ascend, as partition() and global_ids() give them) — are re-sent at
+        their CURRENT positions into the same ghost slots of the neighbours.  No selection, ids and list untouched.
+        Every rank calls it; returns the assembly buffers.  (`nl` is unused here: the peer-store transport keeps
+        the recorded face set in the handle.)"""
+        if self.world == 1:
+            return q_owned, self._gall, q_owned.shape[0]
+        if self._last is None:
+            raise _lib.NlistError(_lib.ERR_STATE, "refresh() needs an exchange (a build) first")
+        n = q_owned.shape[0]
+        ctx = torch.cuda.stream(stream) if (stream is not None and q_owned.is_cuda) else _null()
+        with ctx:
+            if q_owned.data_ptr() != self._qall.data_ptr():
+                self._qall[:n].copy_(q_owned)
+            gid_owned = self._gall[:n]
+            peers = [p for p in (self.rank - 1, self.rank + 1) if 0 <= p < self.world]
+            cap = self._sq[peers[0]].shape[0]
+            ops, at = [], n
+            for p in peers:
+                k = int(min(int(self._cnt[p][0]), cap))  # records the last exchange sent to p (host read: rare call)
+                if k > 0:
+                    idx = torch.searchsorted(gid_owned, self._sg[p][:k])
+                    self._sq[p][:k] = q_owned[idx]
+                ops.append(dist.P2POp(dist.isend, self._sq[p], p, group=self.group))
+                ops.append(dist.P2POp(dist.irecv, self._qall[at:at + cap], p, group=self.group))
+                at += cap
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        self._last = (self._qall, self._gall, n)
+        return self._last
+
     def owned_view(self, n_owned: int, dtype=torch.float64, device=None):
         """(positions, global ids) views of the first n_owned slots of the assembly buffers: a caller that keeps its
         particles there saves the device-to-device copy of every exchange (the buffers are allocated here)."""
@@ -497,7 +530,9 @@ class PeerSlabDecomposition(SlabDecomposition):
         the last build of `nl` recorded into the same ghost slots of the neighbours and wait for this rank's own ghosts
         (nlb200_halo_refresh).  Every rank calls it; returns the assembly buffers (owned records + refreshed ghosts).
         After consuming the ghosts call done() — the neighbours may then overwrite them."""
-        if not (self.uses_peer_stores() and self._synced_handle is nl):
+        if not self.uses_peer_stores():
+            return super().refresh(nl, q_owned, stream)  # the send/recv fallback
+        if self._synced_handle is not nl:
             raise _lib.NlistError(_lib.ERR_STATE, "refresh() needs a build of this handle with the folded exchange first")
         n = q_owned.shape[0]
         ctx = torch.cuda.stream(stream) if stream is not None else _null()

@@ -101,6 +101,42 @@ def test_slab_decomposition_matches_single_process(world):
     mp.spawn(_worker, args=(world, _free_port()), nprocs=world, join=True)
 
 
+def _refresh_worker(rank: int, world: int, port: int):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from md_neighbor_list_b200.parallel import SlabDecomposition
+        q, box = _global_system(world)
+        dec = SlabDecomposition(world, rank, box, SL, axis=2)
+        q_own, gid_own = dec.partition(q)
+        qa0, ga0, n0 = dec.exchange(torch.from_numpy(q_own), torch.from_numpy(gid_own))
+        present0 = ~torch.isnan(qa0[:, 0])
+        ga0 = ga0.clone()
+        # the particles move a little in x and y (the list would stay valid): the same face set, new positions
+        rng = np.random.default_rng(1)
+        q_new = q.copy()
+        q_new[:, :2] += (rng.random((q.shape[0], 2)) - 0.5) * 0.1
+        qa1, ga1, n1 = dec.refresh(None, torch.from_numpy(np.ascontiguousarray(q_new[gid_own])))
+        assert n1 == n0 and torch.equal(ga1, ga0), "ids and slots must not change"
+        present1 = ~torch.isnan(qa1[:, 0])
+        assert torch.equal(present1, present0)
+        ghosts = torch.nonzero(present1[n0:]).flatten() + n0
+        assert ghosts.numel() > 0
+        want = torch.from_numpy(q_new)[ga1[ghosts].long()]
+        assert torch.equal(qa1[ghosts], want), "a ghost slot must hold its particle's current position"
+        assert torch.equal(qa1[:n0], torch.from_numpy(np.ascontiguousarray(q_new[gid_own])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_refresh_resends_the_recorded_face_set(world):
+    """SURVEY.md §8f f2 on the send/recv transport (gloo here, NCCL on the device): between two builds the ghosts are
+    refreshed in place — same slots, same ids, current positions."""
+    mp.spawn(_refresh_worker, args=(world, _free_port()), nprocs=world, join=True)
+
+
 def test_slab_thinner_than_search_length_is_rejected():
     from md_neighbor_list_b200.parallel import SlabDecomposition
     with pytest.raises(ValueError):
