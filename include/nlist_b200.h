@@ -79,11 +79,13 @@ typedef enum {
   NLB200_OPT_EXACT_ONLY = 4,
   /* 1 (default): replay the build as a CUDA graph when (q, n, stream) repeat. 0: plain launches. */
   NLB200_OPT_USE_GRAPH = 5,
-  /* search / emission pair, for tuning and ablation.  0 (default): run masks for FULL lists, pair masks for HALF
-   * lists, row masks once a cell may hold more than 256 particles.  1: one CTA per cell, every test evaluated twice
+  /* search / emission pair, for tuning and ablation.  0 (default): run masks for FULL and HALF lists (emission with
+   * the partner ids gathered from global memory below 2^20 particles, through a shared-memory window from there on),
+   * row masks once a cell may hold more than 256 particles.  1: one CTA per cell, every test evaluated twice
    * (count, fill; also what NLB200_OPT_EXACT_ONLY runs).  2: pair masks.  4: pair masks, HALF rows filtered by id in
-   * the emission.  5, 6: row masks.  7: pair masks with 64-bit mask indices.  8: run masks.  100 + p: p work units
-   * per cell.  Every variant produces the same rows in the same order. */
+   * the emission.  5, 6: row masks.  7: pair masks with 64-bit mask indices.  8: run masks.  9 / 10: run masks with
+   * the gathering / the window emission forced.  100 + p (pair masks), 200 + p (run masks): p work units per cell.
+   * Every variant produces the same rows in the same order. */
   NLB200_OPT_KERNEL_VARIANT = 6,
   /* 1: record a CUDA event between the stages of every build on the build's stream (disables graph replay);
    * read the per-stage device times with nlb200_get_stage_times.  The reference's counterpart is
